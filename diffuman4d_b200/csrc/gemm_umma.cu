@@ -1,0 +1,395 @@
+// tcgen05 (UMMA) GEMM / implicit-GEMM 3x3 convolution for sm_100a.
+//
+//   D[M, N] = A[M, K] * W[N, K]^T  (+bias[N]) (+rowvec[image(m), N]) (+residual[M, N])   -> bf16
+//
+// * operands are bf16, K-major, staged by TMA into 128B-swizzled shared memory (4-stage mbarrier ring)
+// * one elected thread issues tcgen05.mma (M=128, N=block_n<=256, K=16) with fp32 accumulators in TMEM
+// * accumulators are double-buffered in TMEM (2 x 256 columns) so the epilogue of tile i overlaps the
+//   main loop of tile i+1; the kernel is persistent (grid = #SMs), tiles are walked n-fastest so CTAs
+//   that run concurrently share the same A rows through L2
+// * "conv" mode turns the A loader into an implicit-GEMM gather: the A tile for k-block (tap, c0) is a
+//   4-D TMA box {64 ch, BW, BH, BN} of the NHWC activation at spatial offset (ky-1, kx-1); out-of-bounds
+//   rows/cols are zero-filled by TMA, which is exactly the conv's zero padding.  K = 9*Cin, weights are
+//   pre-laid-out as [Cout][tap][Cin].
+// * "two-source" mode reads the first kb_split k-blocks from A and the rest from A2 (a channel concat
+//   that is never materialised: resnet shortcut 1x1 conv over [hidden | skip]).
+// * epilogue options: +bias (fp32), +per-image row vector (time-embedding projection), +residual,
+//   GEGLU (a * gelu_erf(g), weights pre-interleaved so one N tile holds matching a/g columns).
+//
+// Replaces, on the reference path: F.linear / 1x1 conv / 3x3 conv calls of diffusers ResnetBlock2D,
+// Attention, FeedForward, Transformer2DModel (reference call sites: unet_multiview_blocks.py:274,423,585,
+// transformer_multiview.py:46-77, attention.py:73,116,142).
+#include "kernels.h"
+
+namespace d4d {
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;
+constexpr int STAGES = 4;
+constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;     // 16 KB
+constexpr int B_BYTES_MAX = 256 * BLOCK_K * 2;     // 32 KB
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES_MAX; // 48 KB
+constexpr int NUM_THREADS = 192;                   // warp0 TMA, warp1 MMA(+TMEM alloc), warps2-5 epilogue
+constexpr int TMEM_COLS = 512;
+constexpr int ACC_STRIDE = 256;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+
+struct TileCoord {
+  int m0;          // plain: first row.  conv: unused
+  int n_img0, y0, x0;
+};
+
+__device__ __forceinline__ void tile_coords(const GemmKernelArgs& a, int m_tile, TileCoord& t) {
+  if (a.mode == 0) {
+    t.m0 = m_tile * BLOCK_M;
+    t.n_img0 = t.y0 = t.x0 = 0;
+  } else {
+    int tx = m_tile % a.tiles_x;
+    int r = m_tile / a.tiles_x;
+    int ty = r % a.tiles_y;
+    int tn = r / a.tiles_y;
+    t.m0 = 0;
+    t.x0 = tx * a.BW;
+    t.y0 = ty * a.BH;
+    t.n_img0 = tn * a.BN;
+  }
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_a2,
+                 const __grid_constant__ CUtensorMap tmap_b, const GemmKernelArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment for the 128B swizzle atoms
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* full = bars;               // [STAGES]
+  uint64_t* empty = bars + STAGES;     // [STAGES]
+  uint64_t* tfull = bars + 2 * STAGES; // [2]
+  uint64_t* tempty = tfull + 2;        // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = a.m_tiles * a.n_tiles;
+  const uint32_t b_bytes = static_cast<uint32_t>(a.block_n) * BLOCK_K * 2;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    if (a.kb_split < a.k_blocks) tma_prefetch_desc(&tmap_a2);
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m_tile = tile / a.n_tiles;
+        const int n_tile = tile % a.n_tiles;
+        TileCoord tc;
+        tile_coords(a, m_tile, tc);
+        const int n0 = n_tile * a.block_n;
+        for (int kb = 0; kb < a.k_blocks; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * STAGE_BYTES;
+          uint8_t* sb = sa + A_BYTES;
+          mbar_expect_tx(&full[stage], A_BYTES + b_bytes);
+          if (a.mode == 0) {
+            if (kb < a.kb_split) tma_load_2d(sa, &tmap_a, &full[stage], kb * BLOCK_K, tc.m0);
+            else tma_load_2d(sa, &tmap_a2, &full[stage], (kb - a.kb_split) * BLOCK_K, tc.m0);
+            tma_load_2d(sb, &tmap_b, &full[stage], kb * BLOCK_K, n0);
+          } else {
+            const int tap = kb / a.cin_blocks;
+            const int cb = kb - tap * a.cin_blocks;
+            const int ky = tap / 3, kx = tap - ky * 3;
+            tma_load_4d(sa, &tmap_a, &full[stage], cb * BLOCK_K, tc.x0 + kx - 1, tc.y0 + ky - 1, tc.n_img0);
+            tma_load_2d(sb, &tmap_b, &full[stage], tap * a.Cin + cb * BLOCK_K, n0);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc = make_idesc_bf16(BLOCK_M, a.block_n, 0, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      if (lane == 0) {
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * ACC_STRIDE;
+        for (int kb = 0; kb < a.k_blocks; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+          const uint32_t sb = sa + A_BYTES;
+          const uint64_t adesc = make_smem_desc(sa, 0, 1024, 2);
+          const uint64_t bdesc = make_smem_desc(sb, 0, 1024, 2);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / 16; ++k) {
+            // advancing 16 bf16 along K inside the 128B swizzle atom = +32 bytes = +2 in the (addr>>4) field
+            umma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull[acc]);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===================== epilogue (warps 2..5 -> TMEM lane quarter warp%4) =====================
+    const int q = warp & 3;
+    const int r = q * 32 + lane;  // row within the 128-row tile
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int m_tile = tile / a.n_tiles;
+      const int n_tile = tile % a.n_tiles;
+      TileCoord tc;
+      tile_coords(a, m_tile, tc);
+      const int n0 = n_tile * a.block_n;
+
+      long long row;  // output row (pixel/token index)
+      int img;        // image index for the per-image row vector
+      bool valid;
+      if (a.mode == 0) {
+        row = static_cast<long long>(tc.m0) + r;
+        valid = row < a.M;
+        img = a.rows_per_image > 0 ? static_cast<int>(row / a.rows_per_image) : 0;
+      } else {
+        const int bx = r % a.BW;
+        const int rr = r / a.BW;
+        const int by = rr % a.BH;
+        const int bn = rr / a.BH;
+        const int x = tc.x0 + bx, y = tc.y0 + by, n = tc.n_img0 + bn;
+        valid = (x < a.W) && (y < a.H) && (n < a.n_img);
+        row = (static_cast<long long>(n) * a.H + y) * a.W + x;
+        img = n;
+      }
+
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + acc * ACC_STRIDE + (static_cast<uint32_t>(q * 32) << 16);
+
+      if (!a.geglu) {
+        const int chunks = a.block_n / 16;
+        for (int c = 0; c < chunks; ++c) {
+          uint32_t v[16];
+          tmem_ld16(taddr + c * 16, v);
+          tmem_ld_wait();
+          if (valid) {
+            const int col = n0 + c * 16;
+            float f[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
+            if (a.bias) {
+              const float4* bp = reinterpret_cast<const float4*>(a.bias + col);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                float4 b = __ldg(bp + i);
+                f[4 * i] += b.x; f[4 * i + 1] += b.y; f[4 * i + 2] += b.z; f[4 * i + 3] += b.w;
+              }
+            }
+            if (a.rowvec) {
+              const uint4* rp = reinterpret_cast<const uint4*>(a.rowvec + static_cast<size_t>(img) * a.ld_rowvec + col);
+#pragma unroll
+              for (int i = 0; i < 2; ++i) {
+                uint4 u = __ldg(rp + i);
+                float2 p;
+                p = unpack_bf16x2(u.x); f[8 * i] += p.x; f[8 * i + 1] += p.y;
+                p = unpack_bf16x2(u.y); f[8 * i + 2] += p.x; f[8 * i + 3] += p.y;
+                p = unpack_bf16x2(u.z); f[8 * i + 4] += p.x; f[8 * i + 5] += p.y;
+                p = unpack_bf16x2(u.w); f[8 * i + 6] += p.x; f[8 * i + 7] += p.y;
+              }
+            }
+            if (a.act == 1) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) f[i] = silu_f(f[i]);
+            }
+            if (a.out_scale != 1.0f) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) f[i] *= a.out_scale;
+            }
+            if (a.residual) {
+              const uint4* rp = reinterpret_cast<const uint4*>(a.residual + static_cast<size_t>(row) * a.ld_res + col);
+#pragma unroll
+              for (int i = 0; i < 2; ++i) {
+                uint4 u = rp[i];
+                float2 p;
+                p = unpack_bf16x2(u.x); f[8 * i] += p.x; f[8 * i + 1] += p.y;
+                p = unpack_bf16x2(u.y); f[8 * i + 2] += p.x; f[8 * i + 3] += p.y;
+                p = unpack_bf16x2(u.z); f[8 * i + 4] += p.x; f[8 * i + 5] += p.y;
+                p = unpack_bf16x2(u.w); f[8 * i + 6] += p.x; f[8 * i + 7] += p.y;
+              }
+            }
+            uint4* op = reinterpret_cast<uint4*>(a.out + static_cast<size_t>(row) * a.ldo + col);
+            uint4 o0, o1;
+            o0.x = pack_bf16x2(f[0], f[1]);   o0.y = pack_bf16x2(f[2], f[3]);
+            o0.z = pack_bf16x2(f[4], f[5]);   o0.w = pack_bf16x2(f[6], f[7]);
+            o1.x = pack_bf16x2(f[8], f[9]);   o1.y = pack_bf16x2(f[10], f[11]);
+            o1.z = pack_bf16x2(f[12], f[13]); o1.w = pack_bf16x2(f[14], f[15]);
+            op[0] = o0;
+            op[1] = o1;
+          }
+        }
+      } else {
+        // GEGLU: this N tile holds [a (block_n/2 cols) | g (block_n/2 cols)] for output cols
+        // n_tile*block_n/2 .. +block_n/2
+        const int half = a.block_n / 2;
+        const int chunks = half / 16;
+        for (int c = 0; c < chunks; ++c) {
+          uint32_t va[16], vg[16];
+          tmem_ld16(taddr + c * 16, va);
+          tmem_ld16(taddr + half + c * 16, vg);
+          tmem_ld_wait();
+          if (valid) {
+            const int wcol = n0 + c * 16;  // column in the (interleaved) weight/bias space
+            float fa[16], fg[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { fa[i] = __uint_as_float(va[i]); fg[i] = __uint_as_float(vg[i]); }
+            if (a.bias) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                fa[i] += __ldg(a.bias + wcol + i);
+                fg[i] += __ldg(a.bias + wcol + half + i);
+              }
+            }
+            float o[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = fa[i] * gelu_erf_f(fg[i]);
+            const int ocol = n_tile * half + c * 16;
+            uint4* op = reinterpret_cast<uint4*>(a.out + static_cast<size_t>(row) * a.ldo + ocol);
+            uint4 o0, o1;
+            o0.x = pack_bf16x2(o[0], o[1]);   o0.y = pack_bf16x2(o[2], o[3]);
+            o0.z = pack_bf16x2(o[4], o[5]);   o0.w = pack_bf16x2(o[6], o[7]);
+            o1.x = pack_bf16x2(o[8], o[9]);   o1.y = pack_bf16x2(o[10], o[11]);
+            o1.z = pack_bf16x2(o[12], o[13]); o1.w = pack_bf16x2(o[14], o[15]);
+            op[0] = o0;
+            op[1] = o1;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+}  // namespace
+
+int gemm_prepare(const GemmDesc& d, GemmLaunch* L) {
+  D4D_REQUIRE(d.N % 16 == 0, "GEMM N must be a multiple of 16");
+  D4D_REQUIRE(d.out != nullptr && d.A != nullptr && d.Wt != nullptr, "null operand");
+  GemmKernelArgs& a = L->args;
+  memset(&a, 0, sizeof(a));
+  const int bn = d.block_n > 0 ? d.block_n : gemm_pick_block_n(d.N, d.geglu ? 32 : 16);
+  D4D_REQUIRE(bn >= 16 && d.N % bn == 0 && bn % (d.geglu ? 32 : 16) == 0, "no valid block_n");
+  a.block_n = bn;
+  a.n_tiles = d.N / bn;
+  a.N = d.N;
+  a.bias = d.bias;
+  a.rowvec = d.rowvec;
+  a.ld_rowvec = d.ld_rowvec;
+  a.rows_per_image = d.rows_per_image;
+  a.residual = d.residual;
+  a.ld_res = d.ld_res;
+  a.out = d.out;
+  a.ldo = d.ldo;
+  a.geglu = d.geglu;
+  a.act = d.act;
+  a.out_scale = d.out_scale;
+  D4D_REQUIRE(d.ldo % 8 == 0 && (d.residual == nullptr || d.ld_res % 8 == 0) &&
+              (d.rowvec == nullptr || d.ld_rowvec % 8 == 0), "leading dimensions must be multiples of 8");
+
+  if (!d.conv) {
+    D4D_REQUIRE(d.K1 > 0 && d.K1 % 8 == 0 && d.K2 % 8 == 0, "K must be a multiple of 8");
+    D4D_REQUIRE(d.A2 == nullptr || d.K1 % BLOCK_K == 0, "two-source GEMM needs K1 % 64 == 0");
+    a.mode = 0;
+    a.M = d.M;
+    a.m_tiles = (d.M + BLOCK_M - 1) / BLOCK_M;
+    a.kb_split = (d.K1 + BLOCK_K - 1) / BLOCK_K;
+    const int kb2 = d.A2 ? (d.K2 + BLOCK_K - 1) / BLOCK_K : 0;
+    a.k_blocks = a.kb_split + kb2;
+    const int K = d.K1 + (d.A2 ? d.K2 : 0);
+    if (int rc = make_tmap_2d(&L->tmap_a, d.A, d.M, d.K1, d.lda, BLOCK_K, BLOCK_M, 128)) return rc;
+    if (d.A2) {
+      if (int rc = make_tmap_2d(&L->tmap_a2, d.A2, d.M, d.K2, d.lda2, BLOCK_K, BLOCK_M, 128)) return rc;
+    } else {
+      L->tmap_a2 = L->tmap_a;
+    }
+    if (int rc = make_tmap_2d(&L->tmap_b, d.Wt, d.N, K, K, BLOCK_K, bn, 128)) return rc;
+  } else {
+    D4D_REQUIRE(d.Cin % 8 == 0, "conv Cin must be a multiple of 8");
+    a.mode = 1;
+    a.H = d.H; a.W = d.W; a.n_img = d.n_img; a.Cin = d.Cin;
+    a.M = d.n_img * d.H * d.W;
+    a.cin_blocks = (d.Cin + BLOCK_K - 1) / BLOCK_K;
+    a.k_blocks = 9 * a.cin_blocks;
+    a.kb_split = a.k_blocks;
+    // spatial tile: BW x BH x BN = 128 output pixels
+    int bw = 16; while (bw > d.W) bw >>= 1;
+    int bh = 128 / bw; while (bh > d.H && bh > 1) bh >>= 1;
+    // H, W need not be powers of two: the tile may overhang, TMA zero-fills and the epilogue masks
+    int bnimg = 128 / (bw * bh);
+    D4D_REQUIRE(bw * bh * bnimg == 128 && bnimg <= 256, "conv tile shape");
+    a.BW = bw; a.BH = bh; a.BN = bnimg;
+    a.tiles_x = (d.W + bw - 1) / bw;
+    a.tiles_y = (d.H + bh - 1) / bh;
+    const int tiles_n = (d.n_img + bnimg - 1) / bnimg;
+    a.m_tiles = a.tiles_x * a.tiles_y * tiles_n;
+    if (int rc = make_tmap_nhwc(&L->tmap_a, d.A, d.n_img, d.H, d.W, d.Cin, BLOCK_K, bw, bh, bnimg, 128)) return rc;
+    L->tmap_a2 = L->tmap_a;
+    if (int rc = make_tmap_2d(&L->tmap_b, d.Wt, d.N, 9ull * d.Cin, 9ull * d.Cin, BLOCK_K, bn, 128)) return rc;
+  }
+  int dev = 0, sms = 0;
+  D4D_CUDA_OK(cudaGetDevice(&dev));
+  D4D_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int total = a.m_tiles * a.n_tiles;
+  L->grid = total < sms ? total : sms;
+  return 0;
+}
+
+int gemm_run(const GemmLaunch& L, cudaStream_t stream) {
+  static bool attr_set[64] = {};
+  if (int rc = ensure_dyn_smem(gemm_umma_kernel, SMEM_BYTES, attr_set)) return rc;
+  gemm_umma_kernel<<<L.grid, NUM_THREADS, SMEM_BYTES, stream>>>(L.tmap_a, L.tmap_a2, L.tmap_b, L.args);
+  D4D_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+double gemm_flops(const GemmLaunch& L) {
+  return 2.0 * static_cast<double>(L.args.M) * L.args.N * (static_cast<double>(L.args.k_blocks) * BLOCK_K);
+}
+
+}  // namespace d4d

@@ -1,0 +1,181 @@
+// Internal kernel-launcher interface shared by the op-level C-ABI (d4d_api.cu) and the UNet
+// executor (unet.cu).  Every launcher returns 0 on success, non-zero after d4d::set_error().
+#pragma once
+#include <string.h>
+
+#include "common.cuh"
+
+namespace d4d {
+
+// --------------------------------------------------------------------------------------------
+// tcgen05 GEMM / implicit-GEMM conv3x3  (gemm_umma.cu)
+// --------------------------------------------------------------------------------------------
+struct GemmKernelArgs {
+  int M, N, k_blocks, block_n, n_tiles, m_tiles;
+  int mode;      // 0 plain, 1 conv3x3 (stride 1, pad 1, NHWC)
+  int kb_split;  // plain: k-blocks served by A (rest by A2)
+  int H, W, n_img, Cin, cin_blocks, BW, BH, BN, tiles_x, tiles_y;
+  const float* bias;  // [N] fp32 or null
+  const bf16* rowvec; // [images, ld_rowvec] bf16 or null (added to every row of image row/rows_per_image)
+  int ld_rowvec, rows_per_image;
+  const bf16* residual;
+  int ld_res;
+  bf16* out;
+  int ldo;
+  int geglu;
+  int act;          // 0 none, 1 SiLU applied to (acc + bias + rowvec) before scale/residual
+  float out_scale;  // multiplies (acc + bias + rowvec) after the activation
+};
+
+struct GemmDesc {
+  // plain: A [M, K1] (lda), optional second source A2 [M, K2] (lda2) concatenated along K
+  const bf16* A = nullptr;
+  int lda = 0, K1 = 0;
+  const bf16* A2 = nullptr;
+  int lda2 = 0, K2 = 0;
+  const bf16* Wt = nullptr;  // [N, K] row-major (K contiguous); conv: [N][9][Cin]
+  int M = 0, N = 0;
+  const float* bias = nullptr;
+  const bf16* rowvec = nullptr;
+  int ld_rowvec = 0, rows_per_image = 0;
+  const bf16* residual = nullptr;
+  int ld_res = 0;
+  bf16* out = nullptr;
+  int ldo = 0;
+  int geglu = 0;
+  int act = 0;
+  float out_scale = 1.0f;
+  int block_n = 0;  // 0 = auto
+  // conv3x3: A is NHWC [n_img, H, W, Cin]
+  int conv = 0, n_img = 0, H = 0, W = 0, Cin = 0;
+};
+
+struct GemmLaunch {
+  CUtensorMap tmap_a, tmap_a2, tmap_b;
+  GemmKernelArgs args;
+  int grid;
+};
+
+// largest divisor of N that is a multiple of `mult` and <= 256 (0 if none)
+inline int gemm_pick_block_n(int N, int mult) {
+  int best = 0;
+  for (int bn = mult; bn <= 256; bn += mult)
+    if (N % bn == 0) best = bn;
+  return best;
+}
+int gemm_prepare(const GemmDesc& d, GemmLaunch* L);
+int gemm_run(const GemmLaunch& L, cudaStream_t stream);
+double gemm_flops(const GemmLaunch& L);
+
+// --------------------------------------------------------------------------------------------
+// tcgen05 flash attention forward (attention_umma.cu)
+//   q/k/v are column slices of one row-major [tokens, ld] bf16 matrix (the fused QKV GEMM output);
+//   head hd of batch b covers rows [b*S, (b+1)*S) and columns [hd*D, (hd+1)*D) of each slice.
+// --------------------------------------------------------------------------------------------
+struct AttnDesc {
+  const bf16* q = nullptr;
+  const bf16* k = nullptr;
+  const bf16* v = nullptr;
+  int ld_qkv = 0;
+  bf16* out = nullptr;  // [tokens, ld_out]
+  int ld_out = 0;
+  int batch = 0, seq = 0, heads = 0, head_dim = 0;
+  float scale = 0.f;  // softmax scale (head_dim^-0.5)
+};
+struct AttnLaunch {
+  CUtensorMap tmap_q, tmap_k, tmap_v;
+  AttnDesc d;
+  int grid_x, grid_y;
+  int variant;
+};
+int attn_prepare(const AttnDesc& d, AttnLaunch* L);
+int attn_run(const AttnLaunch& L, cudaStream_t stream);
+double attn_flops(const AttnDesc& d);
+
+// --------------------------------------------------------------------------------------------
+// HBM-bound kernels (norm.cu, elementwise.cu)
+// --------------------------------------------------------------------------------------------
+// GroupNorm over NHWC tokens [n_img, hw, C1 (+C2)] (optional virtual channel concat of two sources),
+// fused affine + optional SiLU; writes bf16 [n_img*hw, C1+C2].  partials: fp32 scratch
+// [n_img * splits * groups * 3].
+int groupnorm_splits(int hw);
+int groupnorm_run(const bf16* x1, int C1, const bf16* x2, int C2, int n_img, int hw, int groups, float eps,
+                  const float* gamma, const float* beta, int silu, bf16* out, float* partials, cudaStream_t stream);
+// LayerNorm over rows of width C (C % 8 == 0, C <= 2048)
+int layernorm_run(const bf16* x, int rows, int C, float eps, const float* gamma, const float* beta, bf16* out,
+                  cudaStream_t stream);
+
+// sinusoidal embedding (flip_sin_to_cos / freq_shift) of integer/real positions -> bf16 [n, dim]
+int sinusoid_run(const float* pos, int n, int dim, int flip, float freq_shift, bf16* out, cudaStream_t stream);
+int sinusoid_i64_run(const long long* pos, int n, int dim, int flip, float freq_shift, bf16* out, cudaStream_t stream);
+int silu_run(const bf16* x, long long n, bf16* out, cudaStream_t stream);
+// im2col of an NCHW tensor for a 3x3 pad-1 conv: out[pixel, tap*cin_pad + c] zero-padded to KP columns
+int im2col_nchw_run(const bf16* x, int n, int Cin, int H, int W, int cin_pad, int KP, bf16* out, cudaStream_t stream);
+// [n*hw, ld] (first C columns) -> NCHW [n, C, hw]
+int nhwc_to_nchw_run(const bf16* x, int ld, int n, int C, int hw, bf16* out, cudaStream_t stream);
+// direct small-channel conv (pose encoder): NHWC (or NCHW input when in_nchw), pad 1, optional SiLU
+int direct_conv_run(const bf16* x, int in_nchw, int n, int Cin, int H, int W, const bf16* w /*[k*k][Cin][Cout]*/,
+                    const float* bias, int Cout, int ksize, int stride, int silu, float out_scale, bf16* out_nhwc,
+                    cudaStream_t stream);
+// nearest x2 upsample NHWC
+int upsample2x_run(const bf16* x, int n, int H, int W, int C, bf16* out, cudaStream_t stream);
+// generic NHWC im2col, pad 1: [n,H,W,C] -> [n*Ho*Wo, k*k*C]
+int im2col_nhwc_run(const bf16* x, int n, int H, int W, int C, int ksize, int stride, bf16* out, cudaStream_t stream);
+
+// a-1 input assembly (pipeline_diffuman4d.py:373-395), writes NCHW [2F or F, Cin, h, w] + timesteps
+struct AssembleArgs {
+  bf16* latents;            // [F,4,h,w]  (cond frames are overwritten in place like the reference)
+  const bf16* pixel;        // [F,4,h,w]
+  const bf16* plucker;      // [F,6,h,w]
+  const bf16* skel_latents; // [F,4,h,w] or null (only when the pose encoder is disabled)
+  const bf16* mask;         // [F,1,h,w]
+  const long long* timestep_indices;  // [F] (device)
+  const long long* timesteps_table;   // [n_steps] (device)
+  int n_steps;
+  int F, h, w, cfg;
+  bf16* sample;             // out [(cfg?2:1)*F, Cin, h, w]
+  long long* timestep_out;  // out [(cfg?2:1)*F]
+};
+int assemble_input_run(const AssembleArgs& a, cudaStream_t stream);
+// CFG-negative skeleton batch for the pose encoder: out[0:F] = -1, out[F:2F] = skeletons
+int cfg_skeleton_run(const bf16* skel, long long per_frame_elems, int F, bf16* out, cudaStream_t stream);
+
+// a-13 + a-14: CFG combine + per-frame DDIM step (pipeline_diffuman4d.py:408-423)
+struct DdimArgs {
+  const bf16* noise;        // [(cfg?2:1)*F,4,h,w]
+  const bf16* latents;      // [F,4,h,w]
+  const bf16* mask;         // [F,1,h,w]  (cond frame <=> mask[f,0,0,0]==0)
+  const long long* timestep_indices;  // [F]
+  const long long* timesteps_table;   // [n_steps]
+  const float* alphas_cumprod;        // [T]
+  int n_steps, T;
+  float final_alpha_cumprod;
+  int F, chw, hw, cfg;
+  float guidance;
+  int prediction_type;      // 0 epsilon, 1 v_prediction, 2 sample
+  int clip_sample;
+  float clip_range;
+  int emulate_bf16;         // 1: round after every op like the reference's bf16 eager arithmetic
+  bf16* out;                // [F,4,h,w]
+};
+// ts_out[F]: updated timestep indices (targets +1, cond 0); may not alias a.timestep_indices
+int cfg_ddim_step_run(const DdimArgs& a, long long* ts_out, cudaStream_t stream);
+
+// UMMA operand-encoding probe (probe.cu)
+int probe_umma_run(const bf16* A, const bf16* B, float* D, int N, int K, int a_src, int b_major, uint32_t b_lbo,
+                   uint32_t b_sbo, uint32_t b_kadv, cudaStream_t stream);
+
+// per-device "opt in to large dynamic smem" helper
+template <typename F>
+inline int ensure_dyn_smem(F func, int bytes, bool* done_per_device) {
+  int dev = 0;
+  D4D_CUDA_OK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return 0;
+  if (!done_per_device[dev]) {
+    D4D_CUDA_OK(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    done_per_device[dev] = true;
+  }
+  return 0;
+}
+
+}  // namespace d4d
