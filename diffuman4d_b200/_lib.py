@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_HERE, "libd4d.so")
 # every symbol include/d4d.h declares (tests check the library exports all of them)
 EXPORTS = [
     "d4d_last_error", "d4d_version", "d4d_create", "d4d_destroy", "d4d_load_weight", "d4d_finalize_weights",
-    "d4d_num_weights", "d4d_weight_key", "d4d_unet_forward", "d4d_workspace_bytes", "d4d_forward_launches",
+    "d4d_num_weights", "d4d_weight_key", "d4d_unet_forward", "d4d_profile_forward", "d4d_workspace_bytes", "d4d_forward_launches",
     "d4d_denoise_window", "d4d_assemble_input", "d4d_cfg_ddim_step", "d4d_op_gemm", "d4d_op_conv3x3",
     "d4d_op_attention", "d4d_op_groupnorm", "d4d_op_layernorm", "d4d_op_probe_umma", "d4d_kv_exchange_bytes",
     "d4d_set_peers",
@@ -66,6 +66,8 @@ def lib() -> C.CDLL:
     l.d4d_weight_key.argtypes = [vp, i32]
     l.d4d_weight_key.restype = C.c_char_p
     l.d4d_unet_forward.argtypes = [vp, vp, vp, vp, C.POINTER(C.c_int32), i32, i32, i32, i32, i32, vp, vp]
+    l.d4d_profile_forward.argtypes = [vp, vp, vp, vp, C.POINTER(C.c_int32), i32, i32, i32, i32, i32, vp, vp,
+                                      C.POINTER(C.c_float), C.POINTER(C.c_int32), C.POINTER(C.c_double)]
     l.d4d_workspace_bytes.argtypes = [vp, i32, i32, i32, i32, i32, C.POINTER(C.c_size_t)]
     l.d4d_forward_launches.argtypes = [vp, i32, i32, i32, i32, i32, C.POINTER(C.c_int)]
     l.d4d_denoise_window.argtypes = [vp, vp, vp, vp, vp, vp, vp, C.POINTER(D4DSched), f32, i32, i32, i32, i32, i32, vp]

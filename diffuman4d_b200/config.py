@@ -102,8 +102,8 @@ class UNetConfig:
 
     @classmethod
     def tiny(cls, **kw) -> "UNetConfig":
-        """Small channel counts for CPU-speed tests (same topology, head_dim 32/64)."""
-        base = dict(block_out_channels=(64, 128, 256, 256), attention_head_dim=(2, 2, 4, 4))
+        """Small channel counts for CPU-speed tests (same topology, head_dim 64)."""
+        base = dict(block_out_channels=(64, 128, 256, 256), attention_head_dim=(1, 2, 4, 4))
         base.update(kw)
         return cls(**base)
 

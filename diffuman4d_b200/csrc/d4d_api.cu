@@ -134,6 +134,19 @@ int d4d_unet_forward(d4d_handle* h, const void* sample, const int64_t* timestep,
   D4D_API_END
 }
 
+int d4d_profile_forward(d4d_handle* h, const void* sample, const int64_t* timestep, const void* skeletons,
+                        const int32_t* domain_ids, int n_domains, int B, int F, int height, int width, void* out,
+                        void* stream, float* ms_by_kind, int32_t* launches_by_kind, double* flops_by_kind) {
+  D4D_API_BEGIN
+  D4D_REQUIRE(h != nullptr, "null handle");
+  DeviceGuard g(h->model->device());
+  return h->model->profile(static_cast<const bf16*>(sample), reinterpret_cast<const long long*>(timestep),
+                           static_cast<const bf16*>(skeletons), domain_ids, n_domains, B, F, height, width,
+                           static_cast<bf16*>(out), static_cast<cudaStream_t>(stream), ms_by_kind, launches_by_kind,
+                           flops_by_kind);
+  D4D_API_END
+}
+
 int d4d_workspace_bytes(d4d_handle* h, int n_domains, int B, int F, int height, int width, size_t* bytes) {
   D4D_API_BEGIN
   D4D_REQUIRE(h != nullptr && bytes != nullptr, "null argument");

@@ -63,6 +63,7 @@ std::string plan_key(const int* dom, int nd, int B, int F, int h, int w) {
 
 Plan::~Plan() {
   if (arena) cudaFree(arena);
+  for (cudaEvent_t e : events) cudaEventDestroy(e);
 }
 WindowBufs::~WindowBufs() {
   cudaFree(sample);
@@ -508,29 +509,33 @@ class PlanBuilder {
     else free_.push_back({o, sz});
   }
 
-  void op(std::function<int(cudaStream_t)> f, int launches = 1) {
+  void op(std::function<int(cudaStream_t)> f, int launches = 1, int kind = 5, double flops = 0.0) {
     p_.launches += launches;
-    if (!dry_) p_.ops.push_back(std::move(f));
+    if (!dry_) {
+      p_.ops.push_back(std::move(f));
+      p_.op_kind.push_back(kind);
+      p_.op_flops.push_back(flops);
+    }
   }
   void gemm(const GemmDesc& d) {
     if (dry_) { p_.launches += 1; return; }
     GemmLaunch L;
     if (int rc = gemm_prepare(d, &L)) { if (!rc_) rc_ = rc; return; }
-    op([L](cudaStream_t s) { return gemm_run(L, s); });
+    op([L](cudaStream_t s) { return gemm_run(L, s); }, 1, d.conv ? 1 : 0, gemm_flops(L));
   }
   void attention(const AttnDesc& d) {
     if (dry_) { p_.launches += 1; return; }
     AttnLaunch L;
     if (int rc = attn_prepare(d, &L)) { if (!rc_) rc_ = rc; return; }
-    op([L](cudaStream_t s) { return attn_run(L, s); });
+    op([L](cudaStream_t s) { return attn_run(L, s); }, 1, 2, attn_flops(d));
   }
   void groupnorm(const bf16* x1, int C1, const bf16* x2, int C2, int n_img, int hw, float eps, const NormW& n, int silu, bf16* out) {
     float* part = gn_partials_;
     const int groups = m_.cfg_.norm_num_groups;
-    op([=](cudaStream_t s) { return groupnorm_run(x1, C1, x2, C2, n_img, hw, groups, eps, n.g, n.b, silu, out, part, s); }, 2);
+    op([=](cudaStream_t s) { return groupnorm_run(x1, C1, x2, C2, n_img, hw, groups, eps, n.g, n.b, silu, out, part, s); }, 2, 3);
   }
   void layernorm(const bf16* x, int rows, int C, const NormW& n, bf16* out) {
-    op([=](cudaStream_t s) { return layernorm_run(x, rows, C, 1e-5f, n.g, n.b, out, s); });
+    op([=](cudaStream_t s) { return layernorm_run(x, rows, C, 1e-5f, n.g, n.b, out, s); }, 1, 4);
   }
 
   // ResnetBlock2D on (xa | xb) -> new buffer   (reference semantics: SURVEY R-1)
@@ -944,6 +949,38 @@ int Model::forward(const bf16* sample, const long long* timestep, const bf16* sk
   p->out = out;
   for (auto& f : p->ops)
     if (int rc = f(stream)) return rc;
+  return 0;
+}
+
+int Model::profile(const bf16* sample, const long long* timestep, const bf16* skeletons, const int* domain_ids, int n_domains,
+                   int B, int F, int h, int w, bf16* out, cudaStream_t stream, float* ms_by_kind, int* launches_by_kind,
+                   double* flops_by_kind) {
+  D4D_REQUIRE(sample && timestep && out && domain_ids && ms_by_kind && launches_by_kind && flops_by_kind, "null argument");
+  Plan* p = nullptr;
+  if (int rc = get_plan(domain_ids, n_domains, B, F, h, w, &p)) return rc;
+  D4D_CUDA_OK(cudaSetDevice(device_));
+  p->sample = sample; p->timestep = timestep; p->skeletons = skeletons; p->out = out;
+  const size_t n = p->ops.size();
+  while (p->events.size() < n + 1) {
+    cudaEvent_t e;
+    D4D_CUDA_OK(cudaEventCreate(&e));
+    p->events.push_back(e);
+  }
+  for (size_t i = 0; i < n; ++i) {
+    D4D_CUDA_OK(cudaEventRecord(p->events[i], stream));
+    if (int rc = p->ops[i](stream)) return rc;
+  }
+  D4D_CUDA_OK(cudaEventRecord(p->events[n], stream));
+  D4D_CUDA_OK(cudaEventSynchronize(p->events[n]));
+  for (int k = 0; k < 6; ++k) { ms_by_kind[k] = 0.f; launches_by_kind[k] = 0; flops_by_kind[k] = 0.0; }
+  for (size_t i = 0; i < n; ++i) {
+    float ms = 0.f;
+    D4D_CUDA_OK(cudaEventElapsedTime(&ms, p->events[i], p->events[i + 1]));
+    const int k = p->op_kind[i];
+    ms_by_kind[k] += ms;
+    launches_by_kind[k] += (k == 3 ? 2 : 1);
+    flops_by_kind[k] += p->op_flops[i];
+  }
   return 0;
 }
 

@@ -46,6 +46,9 @@ struct Plan {
   size_t arena_bytes = 0;
   int launches = 0;
   std::vector<std::function<int(cudaStream_t)>> ops;
+  std::vector<int> op_kind;       // 0 gemm, 1 conv3x3, 2 attention, 3 groupnorm, 4 layernorm, 5 other
+  std::vector<double> op_flops;   // executed FLOPs (incl. tile/head padding) of tensor-core ops
+  std::vector<cudaEvent_t> events; // lazily created by profile()
   // per-call externals, set by Model::forward before running the ops
   const bf16* sample = nullptr;
   const long long* timestep = nullptr;
@@ -75,6 +78,10 @@ class Model {
   int denoise_window(bf16* latents, const bf16* pixel, const bf16* plucker, const bf16* skeletons, const bf16* mask,
                      long long* ts_idx, const d4d_sched& sched, float guidance, int domain, int F, int h, int w,
                      int num_steps, cudaStream_t stream);
+  // per-kind device time (ms) of one forward, measured with CUDA events around every op
+  int profile(const bf16* sample, const long long* timestep, const bf16* skeletons, const int* domain_ids, int n_domains,
+              int B, int F, int h, int w, bf16* out, cudaStream_t stream, float* ms_by_kind, int* launches_by_kind,
+              double* flops_by_kind);
   int get_plan(const int* domain_ids, int n_domains, int B, int F, int h, int w, Plan** out);
   Plan* find_plan(int n_domains, int B, int F, int h, int w);
   const std::vector<std::string>& keys() const { return key_order_; }

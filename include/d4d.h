@@ -89,6 +89,13 @@ const char* d4d_weight_key(d4d_handle* h, int i);
 int d4d_unet_forward(d4d_handle* h, const void* sample, const int64_t* timestep, const void* skeletons,
                      const int32_t* domain_ids, int n_domains, int B, int F, int height, int width, void* out,
                      void* stream);
+/* Same call, but with a CUDA event around every launch; synchronises, then reports the device time (ms), launch
+ * count and executed tensor-core FLOPs per kernel kind: 0 GEMM, 1 conv3x3, 2 attention, 3 GroupNorm, 4 LayerNorm,
+ * 5 other.  Used by bench.py for the live roofline figures. */
+int d4d_profile_forward(d4d_handle* h, const void* sample, const int64_t* timestep, const void* skeletons,
+                        const int32_t* domain_ids, int n_domains, int B, int F, int height, int width, void* out,
+                        void* stream, float* ms_by_kind /*[6]*/, int32_t* launches_by_kind /*[6]*/,
+                        double* flops_by_kind /*[6]*/);
 /* Bytes of activation workspace the plan for this shape owns (allocated lazily, kept in the handle). */
 int d4d_workspace_bytes(d4d_handle* h, int n_domains, int B, int F, int height, int width, size_t* bytes);
 /* Kernel launches one forward of this shape enqueues (0 if the plan does not exist yet). */

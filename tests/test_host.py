@@ -1,0 +1,136 @@
+"""CPU tests of the host-side logic and of the C-ABI boundary (no GPU compute): the shared library loads, exports
+exactly the symbols include/d4d.h declares, and fails loudly without a device."""
+import ctypes as C
+import os
+import re
+
+import pytest
+import torch
+
+from diffuman4d_b200.config import SchedulerConfig, UNetConfig
+from diffuman4d_b200.weights import random_state_dict, state_dict_spec
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def libd4d():
+    from diffuman4d_b200 import build
+    build.build(verbose=False)          # nvcc cross-compiles sm_100a without a GPU
+    from diffuman4d_b200._lib import lib
+    return lib()
+
+
+def test_header_and_library_export_the_same_symbols(libd4d):
+    from diffuman4d_b200._lib import EXPORTS
+    hdr = open(os.path.join(ROOT, "include", "d4d.h")).read()
+    declared = set(re.findall(r"\b(d4d_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(EXPORTS), declared ^ set(EXPORTS)
+    for name in EXPORTS:
+        assert hasattr(libd4d, name), f"libd4d.so does not export {name}"
+    assert libd4d.d4d_version() >= 100
+
+
+def test_library_has_no_libcuda_or_torch_dependency(libd4d):
+    import subprocess
+    from diffuman4d_b200._lib import LIB_PATH
+    out = subprocess.run(["ldd", LIB_PATH], capture_output=True, text=True).stdout
+    assert "libcuda.so" not in out and "libtorch" not in out and "libc10" not in out, out
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="only meaningful on a box without a GPU")
+def test_create_fails_loudly_without_gpu(libd4d):
+    from diffuman4d_b200._lib import D4DError
+    from diffuman4d_b200.unet import B200MultiviewUNet
+    with pytest.raises((D4DError, ValueError)):
+        B200MultiviewUNet(UNetConfig.tiny(), device=0)
+    with pytest.raises(ValueError):
+        B200MultiviewUNet(UNetConfig.tiny(), device="cpu")
+
+
+def test_create_rejects_bad_config(libd4d):
+    from diffuman4d_b200._lib import D4DConfig
+    c = D4DConfig()
+    h = C.c_void_p()
+    assert libd4d.d4d_create(C.byref(c), 0, C.byref(h)) == 1
+    assert b"layers_per_block" in libd4d.d4d_last_error()
+    assert libd4d.d4d_create(None, 0, C.byref(h)) == 1
+
+
+def test_config_validation():
+    with pytest.raises(ValueError):
+        UNetConfig(block_out_channels=(320, 640, 1280))
+    with pytest.raises(ValueError):
+        UNetConfig(attention_head_dim=(7, 10, 20, 20))
+    with pytest.raises(ValueError):
+        UNetConfig(cross_attention_dim=1280)      # would crash at the 320/640 levels in the reference
+    c = UNetConfig.ctor_default()
+    assert [c.head_dim(i) for i in range(4)] == [40, 80, 160, 160] and not c.has_attn2(0)
+    c = UNetConfig.sd21(cross_attention_dim=(320, 640, 1280, 1280))
+    assert c.has_attn2(2) and c.head_dim(0) == 64 and c.time_embed_dim == 1280
+
+
+@pytest.mark.parametrize("cfg", [UNetConfig.tiny(), UNetConfig.tiny(cross_attention_dim=(64, 128, 256, 256),
+                                                                     use_linear_projection=False,
+                                                                     enable_pose_encoder=False, enable_tem_embeds=False,
+                                                                     in_channels=15)])
+def test_weight_key_contract_matches_oracle(cfg):
+    from oracle.unet_oracle import build_oracle
+    sd = build_oracle(cfg).state_dict()
+    spec = state_dict_spec(cfg)
+    assert set(sd) == set(spec)
+    for k, v in sd.items():
+        assert tuple(v.shape) == spec[k], k
+    rs = random_state_dict(cfg, seed=3, dtype=torch.float32)
+    assert set(rs) == set(spec) and rs["pose_encoder.scale"].item() == 2.0 if cfg.enable_pose_encoder else True
+
+
+def test_full_size_spec_counts():
+    spec = state_dict_spec(UNetConfig.sd21())
+    n = sum(torch.Size(s).numel() for s in spec.values())
+    assert 8.0e8 < n < 8.4e8 and len(spec) == 597
+    assert spec["up_blocks.1.resnets.2.conv1.weight"] == (1280, 1920, 3, 3)      # concat-skip input channels
+    assert spec["down_blocks.1.attentions.0.transformer_blocks.0.ff.net.0.proj.weight"] == (5120, 640)
+
+
+def test_scheduler_tables_match_oracle():
+    from diffuman4d_b200.scheduler import DDIMTables
+    from oracle.pipeline_oracle import DDIMOracle
+    for sc in (SchedulerConfig(), SchedulerConfig(prediction_type="v_prediction", set_alpha_to_one=True, steps_offset=0),
+               SchedulerConfig(timestep_spacing="trailing"), SchedulerConfig(beta_schedule="linear", beta_start=1e-4, beta_end=0.02)):
+        a, b = DDIMTables(sc, device="cpu"), DDIMOracle(sc)
+        assert torch.equal(a.alphas_cumprod, b.alphas_cumprod)
+        for n in (12, 18, 36, 60):
+            assert torch.equal(a.set_timesteps(n), b.set_timesteps(n))
+        assert abs(a.final_alpha_cumprod - float(b.final_alpha_cumprod)) == 0
+    with pytest.raises(ValueError):
+        DDIMTables(SchedulerConfig(), device="cpu").set_timesteps(5000)
+
+
+def test_window_builder_matches_oracle():
+    from diffuman4d_b200.pipeline import build_windows
+    from oracle.pipeline_oracle import build_windows as ref
+    mask = torch.ones(48)
+    mask[[1, 13, 25, 37]] = 0
+    tgt, inp = torch.where(mask != 0)[0], torch.where(mask == 0)[0]
+    for kw in (dict(window_size=12, sliding_stride=2), dict(window_size=12, sliding_stride=1, bidirectional=True),
+               dict(window_size=4, sliding_stride=1, sliding_shift=3)):
+        a, b = build_windows(tgt, inp, "spatial", **kw), ref(tgt, inp, "spatial", **kw)
+        assert len(a[0]) == len(b[0]) and all(torch.equal(x, y) for x, y in zip(a[0], b[0]))
+    with pytest.raises(ValueError):
+        build_windows(tgt, inp, "diagonal", 12, 2)
+
+
+def test_loader_config_mapping():
+    from diffuman4d_b200.loader import scheduler_config_from_json, unet_config_from_json
+    c = unet_config_from_json(dict(in_channels=11, attention_head_dim=[5, 10, 20, 20], cross_attention_dim=None,
+                                   use_linear_projection=True, enable_pose_encoder=True, enable_tem_embeds=True))
+    assert c == UNetConfig.sd21()
+    with pytest.raises(NotImplementedError):
+        unet_config_from_json(dict(class_embed_type="timestep", cross_attention_dim=None))
+    with pytest.raises(NotImplementedError):
+        scheduler_config_from_json({"_class_name": "EulerDiscreteScheduler"})
+    s = scheduler_config_from_json({"_class_name": "DDIMScheduler", "beta_schedule": "scaled_linear", "beta_start": 0.00085,
+                                    "beta_end": 0.012, "clip_sample": False, "set_alpha_to_one": False, "steps_offset": 1,
+                                    "prediction_type": "v_prediction"})
+    assert s.prediction_type == "v_prediction" and s.steps_offset == 1
