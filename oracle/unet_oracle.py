@@ -381,14 +381,14 @@ class OracleUNet(nn.Module):
             sample = 2 * sample - 1.0
         if not torch.is_tensor(timestep):
             timestep = torch.tensor([timestep], dtype=torch.int64)
-        timestep = timestep.reshape(-1).expand(sample.shape[0])
+        timestep = timestep.reshape(-1).expand(sample.shape[0]).to(sample.device)
         t_emb = timestep_embedding(timestep, cfg.block_out_channels[0], cfg.flip_sin_to_cos, cfg.freq_shift).to(dtype)
         emb = self.time_embedding(t_emb)
         if cfg.enable_tem_embeds:
             if len(domains) * num_frames != len(emb):
                 raise ValueError(
                     f"num_frames: {num_frames} * len(domains): {len(domains)} != len(emb): {len(emb)}")
-            idx = self.frame_indices(domains, num_frames)
+            idx = self.frame_indices(domains, num_frames, device=sample.device)
             f_emb = timestep_embedding(idx, cfg.block_out_channels[0], True, 0).to(dtype)
             emb = emb + self.temporal_pos_embed(f_emb)
         x = self.conv_in(sample)

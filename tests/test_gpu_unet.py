@@ -128,9 +128,11 @@ def test_assemble_input_bit_exact(cuda, with_skel):
         x_d = torch.empty(B, x_ref.shape[1], h, w, dtype=torch.bfloat16, device="cuda")
         t_d = torch.empty(B, dtype=torch.int64, device="cuda")
         tbl = ts.timesteps.cuda()
-        check(lib().d4d_assemble_input(lat_d.data_ptr(), pix.cuda().data_ptr(), plk.cuda().data_ptr(),
-                                       skl.cuda().data_ptr() if with_skel else None, mask.cuda().data_ptr(),
-                                       ti.cuda().data_ptr(), tbl.data_ptr(), 18, F, h, w, int(cfg_on), x_d.data_ptr(),
+        pix_d, plk_d, msk_d, ti_d = pix.cuda(), plk.cuda(), mask.cuda(), ti.cuda()   # keep the device copies alive
+        skl_d = skl.cuda() if with_skel else None
+        check(lib().d4d_assemble_input(lat_d.data_ptr(), pix_d.data_ptr(), plk_d.data_ptr(),
+                                       skl_d.data_ptr() if with_skel else None, msk_d.data_ptr(),
+                                       ti_d.data_ptr(), tbl.data_ptr(), 18, F, h, w, int(cfg_on), x_d.data_ptr(),
                                        t_d.data_ptr(), torch.cuda.current_stream().cuda_stream))
         torch.cuda.synchronize()
         assert torch.equal(x_d.cpu(), x_ref)
@@ -167,8 +169,9 @@ def test_cfg_ddim_step(cuda, pred):
         out = torch.empty(F, 4, h, w, dtype=torch.bfloat16, device="cuda")
         ti_out = torch.empty(F, dtype=torch.int64, device="cuda")
         s = ts.c_struct(emulate)
-        check(lib().d4d_cfg_ddim_step(noise.cuda().data_ptr(), lat.cuda().data_ptr(), mask.cuda().data_ptr(),
-                                      ti.cuda().data_ptr(), ti_out.data_ptr(), C.byref(s), 2.0, 1, F, h, w,
+        noise_d, lat_d, msk_d, ti_d = noise.cuda(), lat.cuda(), mask.cuda(), ti.cuda()   # keep the device copies alive
+        check(lib().d4d_cfg_ddim_step(noise_d.data_ptr(), lat_d.data_ptr(), msk_d.data_ptr(),
+                                      ti_d.data_ptr(), ti_out.data_ptr(), C.byref(s), 2.0, 1, F, h, w,
                                       out.data_ptr(), torch.cuda.current_stream().cuda_stream))
         torch.cuda.synchronize()
         assert ti_out.cpu().tolist() == [ti[0] + 1, 0, ti[2] + 1, ti[3] + 1, ti[4] + 1]
