@@ -7,13 +7,18 @@
 // and attn2 (per-image).  Q/K/V are read in place from the fused QKV-GEMM output [tokens, 3C] through
 // strided TMA boxes, so "(b t) hw c -> b (t hw) c" and the head split are address arithmetic only.
 //
-// One CTA = 128 query rows of one (batch, head).  Warp roles (192 threads):
-//   warps 0-3  softmax: thread t owns query row t (TMEM lane t): S -> max/exp2/sum -> P (bf16) back to TMEM,
-//              lazy O rescale (only when the running max grows by > 8 in log2 units), final O/l store
-//   warp  4    TMA producer: Q once, then K_0, K_1, V_0, K_2, V_1, ... through a ring of 16 KB*NB slots
-//   warp  5    MMA issuer:   S = Q K_j^T (SS, both K-major), O += P V_j (A = P from TMEM, B = V MN-major)
-// S(j+1) is issued as soon as the softmax warps have pulled S(j) into registers, so the tensor core runs
-// under the exp phase; with head_dim 64 two CTAs are co-resident per SM (256 TMEM columns, ~97 KB smem each).
+// One CTA = 128 query rows of one (batch, head); two CTAs are co-resident per SM at head_dim 64.
+// Warp roles (320 threads):
+//   warps 0-7  softmax.  TMEM lane quarter = warp%4 (row = lane), column half = warp/4: the two warps of a row
+//              quarter split the 128 key columns of S, the 64 packed P columns and the D columns of O.
+//              Each thread pulls its 64 S values into registers with ONE exposed TMEM round trip per tile and
+//              releases S at once (Q.K(j+1) runs under the exp phase).  P = exp2(S*scale - m) is computed with the
+//              running max m of the previous tiles; if the row max grows by more than 8 (log2 units) O and l are
+//              rescaled before the next tile, and only if it would overflow (> 100, always for tile 0) P is
+//              recomputed from the registers with the new max.  Row sums are kept per thread and combined once at
+//              the end.  FMNMX3 / FFMA2 / FADD2 packed math; the masked tail tile is a separate instantiation.
+//   warp  8    TMA producer: Q once, then K_0, K_1, V_0, K_2, V_1, ... through a ring of 16 KB*NB slots
+//   warp  9    MMA issuer:   S = Q K_j^T (SS, both K-major), O += P V_j (A = P bf16 from TMEM, B = V MN-major)
 #include <math.h>
 
 #include "kernels.h"
@@ -24,22 +29,23 @@ namespace {
 
 constexpr int BLOCK_Q = 128;
 constexpr int BLOCK_KV = 128;
-constexpr int ATT_THREADS = 192;
+constexpr int ATT_THREADS = 320;
 constexpr int TILE_BYTES = 128 * 64 * 2;  // one [128 rows][64 ch] swizzled box
 
 template <int NB>
 struct AttCfg {
   static constexpr int D = 64 * NB;
-  static constexpr int SLOT_BYTES = TILE_BYTES * NB;           // one K or V tile
+  static constexpr int SLOT_BYTES = TILE_BYTES * NB;  // one K or V tile
   static constexpr int SLOTS = NB == 3 ? 3 : 5;
   static constexpr int Q_BYTES = TILE_BYTES * NB;
-  static constexpr int SMEM_BYTES = Q_BYTES + SLOTS * SLOT_BYTES + 1024 + 256;
+  static constexpr int XCH_BYTES = 128 * 2 * 4 * 2 + 128 * 2 * 4 + 128;  // tile-max exchange (2 parities) + row sums + redo flags
+  static constexpr int SMEM_BYTES = Q_BYTES + SLOTS * SLOT_BYTES + 1024 + 256 + XCH_BYTES;
   static constexpr int TMEM_COLS = NB == 1 ? 256 : 512;
   static constexpr int COL_S = 0, COL_P = 128, COL_O = 192;
 };
 
 struct AttKernelArgs {
-  int seq, heads, n_kv_tiles;
+  int seq_q, seq_kv, heads, n_kv_tiles;
   float scale_log2;
   bf16* out;
   int ld_out;
@@ -47,8 +53,82 @@ struct AttKernelArgs {
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
-  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+// sm_100a packed-fp32 / 3-input helpers (SASS: FMNMX3, FFMA2, FADD2) -- halve the issue slots of the softmax
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]),
+               "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void pair_barrier(int q) {  // the two warps (64 threads) that share a TMEM lane quarter
+  asm volatile("bar.sync %0, 64;" ::"r"(q + 1) : "memory");
+}
+
+// Row max over 32 S columns held in registers (four independent FMNMX3 chains); kMasked: only columns < valid count
+template <bool kMasked>
+__device__ __forceinline__ void max32(const uint32_t* v, float (&mx)[4], int valid_cols) {
+#pragma unroll
+  for (int i = 0; i < 32; i += 8) {
+    if (!kMasked) {
+      mx[0] = max3(mx[0], __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
+      mx[1] = max3(mx[1], __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+      mx[2] = max3(mx[2], __uint_as_float(v[i + 4]), __uint_as_float(v[i + 5]));
+      mx[3] = max3(mx[3], __uint_as_float(v[i + 6]), __uint_as_float(v[i + 7]));
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (i + k < valid_cols) mx[k & 3] = fmaxf(mx[k & 3], __uint_as_float(v[i + k]));
+    }
+  }
+}
+// e = exp2(s*scale - m) for 32 columns -> 16 packed bf16x2 P columns in TMEM, row-sum share in two f32x2 accumulators
+template <bool kMasked>
+__device__ __forceinline__ void exp32(const uint32_t* v, uint64_t sc2, uint64_t nm2, uint64_t (&lsum)[2], uint32_t p_addr,
+                                      int valid_cols) {
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    uint32_t pk[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int i = h * 8 + k;
+      const uint64_t x = fma2(pack2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), sc2, nm2);
+      float x0, x1;
+      unpack2(x, x0, x1);
+      float e0 = ex2_approx(x0), e1 = ex2_approx(x1);
+      if (kMasked) {
+        if (2 * i >= valid_cols) e0 = 0.f;
+        if (2 * i + 1 >= valid_cols) e1 = 0.f;
+      }
+      pk[k] = pack_bf16x2(e0, e1);
+      lsum[k & 1] = add2(lsum[k & 1], pack2(e0, e1));
+    }
+    tmem_st8(p_addr + h * 8, pk);
+  }
 }
 
 template <int NB>
@@ -61,14 +141,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   uint8_t* sQ = smem;
   uint8_t* sRing = smem + C::Q_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sRing + C::SLOTS * C::SLOT_BYTES);
-  uint64_t* ring_full = bars;                  // [SLOTS]
-  uint64_t* ring_empty = bars + C::SLOTS;      // [SLOTS]
+  uint64_t* ring_full = bars;              // [SLOTS]
+  uint64_t* ring_empty = bars + C::SLOTS;  // [SLOTS]
   uint64_t* q_full = bars + 2 * C::SLOTS;
   uint64_t* s_full = q_full + 1;
   uint64_t* s_free = q_full + 2;
   uint64_t* p_ready = q_full + 3;
   uint64_t* pv_done = q_full + 4;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_full + 5);
+  float* xmax = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);  // [2 parity][128 rows][2 halves]
+  float* xsum = xmax + 2 * 128 * 2;                                                  // [128 rows][2 halves]
+  int* xflag = reinterpret_cast<int*>(xsum + 128 * 2);                               // [2 parity][4 quarters][2 halves]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -76,8 +159,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   const int bh = blockIdx.y;
   const int b = bh / a.heads;
   const int hd = bh - b * a.heads;
-  const int row0 = b * a.seq;               // first token row of this batch in the [tokens, ld] matrix
-  const int col0 = hd * C::D;               // first column of this head inside the q/k/v slice
+  const int q_row0 = b * a.seq_q;    // first query-token row of this batch
+  const int kv_row0 = b * a.seq_kv;  // first key/value-token row of this batch
+  const int col0 = hd * C::D;        // first column of this head inside the q/k/v slice
   const int n_tiles = a.n_kv_tiles;
 
   if (threadIdx.x == 0) {
@@ -87,18 +171,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     }
     mbar_init(q_full, 1);
     mbar_init(s_full, 1);
-    mbar_init(s_free, 4);
-    mbar_init(p_ready, 4);
+    mbar_init(s_free, 8);
+    mbar_init(p_ready, 8);
     mbar_init(pv_done, 1);
     fence_mbar_init();
   }
-  if (warp == 5) tmem_alloc(tmem_slot, C::TMEM_COLS);
+  if (warp == 9) tmem_alloc(tmem_slot, C::TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == 4) {
+  if (warp == 8) {
     // ============================ TMA producer ============================
     if (lane == 0) {
       tma_prefetch_desc(&tmap_q);
@@ -107,7 +191,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       mbar_expect_tx(q_full, C::Q_BYTES);
 #pragma unroll
       for (int nb = 0; nb < NB; ++nb)
-        tma_load_2d(sQ + nb * TILE_BYTES, &tmap_q, q_full, col0 + nb * 64, row0 + q_tile * BLOCK_Q);
+        tma_load_2d(sQ + nb * TILE_BYTES, &tmap_q, q_full, col0 + nb * 64, q_row0 + q_tile * BLOCK_Q);
       int slot = 0;
       uint32_t phase = 0;
       // order of tiles through the ring: K0, K1, V0, K2, V1, ..., K(n-1), V(n-2), V(n-1)
@@ -122,11 +206,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 #pragma unroll
         for (int nb = 0; nb < NB; ++nb)
           tma_load_2d(dst + nb * TILE_BYTES, is_v ? &tmap_v : &tmap_k, &ring_full[slot], col0 + nb * 64,
-                      row0 + j * BLOCK_KV);
+                      kv_row0 + j * BLOCK_KV);
         if (++slot == C::SLOTS) { slot = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     // ============================ MMA issuer ============================
     if (lane == 0) {
       const uint32_t idesc_qk = make_idesc_bf16(BLOCK_Q, BLOCK_KV, 0, 0);
@@ -171,9 +255,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       issue_qk();  // S(0)
       for (int j = 0; j < n_tiles; ++j) {
         if (j + 1 < n_tiles) {
-          mbar_wait(s_free, j & 1);  // softmax has S(j) in registers
+          mbar_wait(s_free, j & 1);  // every softmax thread holds its part of S(j) in registers
           tc_fence_after();
-          issue_qk();                // S(j+1)
+          issue_qk();                // S(j+1) runs under the exp phase of tile j
         }
         mbar_wait(p_ready, j & 1);
         tc_fence_after();
@@ -182,95 +266,117 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     }
   } else {
     // ============================ softmax / correction / epilogue ============================
-    const uint32_t lane_sel = static_cast<uint32_t>(warp * 32) << 16;
-    const uint32_t s_tmem = tmem + C::COL_S + lane_sel;
-    const uint32_t p_tmem = tmem + C::COL_P + lane_sel;
-    const uint32_t o_tmem = tmem + C::COL_O + lane_sel;
-    const int qrow = q_tile * BLOCK_Q + threadIdx.x;  // row within the sequence
-    float m = -INFINITY;  // running max, in scaled log2 units
-    float l = 0.f;
+    const int q = warp & 3;   // TMEM lane quarter
+    const int hf = warp >> 2;  // column half
+    const int r = q * 32 + lane;
+    const uint32_t lane_sel = static_cast<uint32_t>(q * 32) << 16;
+    const uint32_t s_tmem = tmem + C::COL_S + lane_sel + hf * 64;
+    const uint32_t p_tmem = tmem + C::COL_P + lane_sel + hf * 32;
+    const uint32_t o_tmem = tmem + C::COL_O + lane_sel + hf * (C::D / 2);
+    const int qrow = q_tile * BLOCK_Q + r;  // row within the sequence
+    const uint64_t sc2 = pack2(a.scale_log2, a.scale_log2);
+    float m = -INFINITY;      // max used for the exponentials of the NEXT tile (scaled log2 units)
+    float l = 0.f;            // this thread's share of the row sum (its 64 columns of every tile)
+    float alpha_pend = 1.f;   // pending rescale of O and l (applied once P.V of the previous tile has landed)
+
+    // O[:, my half] *= alpha (warp-collective; alpha is per lane/row)
+    auto rescale_o = [&](float alpha) {
+#pragma unroll 1
+      for (int c = 0; c < C::D / 2; c += 16) {
+        uint32_t v[16];
+        tmem_ld16(o_tmem + c, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+        tmem_st16(o_tmem + c, v);
+      }
+    };
     for (int j = 0; j < n_tiles; ++j) {
-      const int valid = min(BLOCK_KV, a.seq - j * BLOCK_KV);
-      mbar_wait(s_full, j & 1);
+      const int valid = min(BLOCK_KV, a.seq_kv - j * BLOCK_KV);
+      const int vcols = valid - hf * 64;  // valid columns inside my half (<= 0 .. >= 64)
+      const bool full = valid == BLOCK_KV;
+      const int par = j & 1;
+      mbar_wait(s_full, par);
       tc_fence_after();
-      // ---- pass 1: row max ----
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld32(s_tmem + c * 32, v);
-        tmem_ld_wait();
-        if (valid == BLOCK_KV) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(v[i]));
-        }
-      }
-      mx *= a.scale_log2;
-      const bool grow = mx > m + 8.0f;
-      const float m_new = grow ? mx : m;
-      if (j > 0) {
-        mbar_wait(pv_done, (j - 1) & 1);  // P and O are free to touch
+      // my 64 columns of S(j) -> registers (one exposed TMEM latency per tile), then release S for Q.K(j+1)
+      uint32_t sv[64];
+      tmem_ld32(s_tmem, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
+      tmem_ld32(s_tmem + 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[32]));
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_free);
+
+      float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+      if (full) { max32<false>(sv, mx, 32); max32<false>(sv + 32, mx, 32); }
+      else { max32<true>(sv, mx, vcols); max32<true>(sv + 32, mx, vcols - 32); }
+      const float tmax = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * a.scale_log2;
+
+      if (j > 0) {  // P and O may only be touched once P.V(j-1) has landed
+        mbar_wait(pv_done, (j - 1) & 1);
         tc_fence_after();
-        if (__any_sync(0xffffffffu, grow)) {
-          const float alpha = grow ? ex2_approx(m - m_new) : 1.0f;
-          l *= alpha;
-#pragma unroll 1
-          for (int c = 0; c < C::D / 16; ++c) {
-            uint32_t v[16];
-            tmem_ld16(o_tmem + c * 16, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
-            tmem_st16(o_tmem + c * 16, v);
-          }
+        if (__any_sync(0xffffffffu, alpha_pend != 1.f)) {  // rescale decided at the end of the previous tile
+          rescale_o(alpha_pend);
+          l *= alpha_pend;
+          alpha_pend = 1.f;
         }
       }
-      m = m_new;
-      // ---- pass 2: P = exp2(S*scale - m), row sum, bf16 pack -> TMEM ----
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld32(s_tmem + c * 32, v);
-        tmem_ld_wait();
-        if (c == 3) {
-          // S(j) is fully in registers: let the MMA warp overwrite it with S(j+1)
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(s_free);
+      uint64_t lsum[2] = {0ull, 0ull};
+      if (j > 0) {  // speculative P with the running max of the previous tiles
+        const uint64_t nm2 = pack2(-m, -m);
+        if (full) { exp32<false>(sv, sc2, nm2, lsum, p_tmem, 32); exp32<false>(sv + 32, sc2, nm2, lsum, p_tmem + 16, 32); }
+        else { exp32<true>(sv, sc2, nm2, lsum, p_tmem, vcols); exp32<true>(sv + 32, sc2, nm2, lsum, p_tmem + 16, vcols - 32); }
+      }
+      const bool ovf = !(tmax <= m + 100.f);  // would overflow with the old max; always true for tile 0 (m = -inf)
+      xmax[(par * 128 + r) * 2 + hf] = tmax;
+      const int warp_ovf = __any_sync(0xffffffffu, ovf) ? 1 : 0;
+      if (lane == 0) xflag[(par * 4 + q) * 2 + hf] = warp_ovf;
+      pair_barrier(q);
+      const float tmax_row = fmaxf(tmax, xmax[(par * 128 + r) * 2 + (hf ^ 1)]);
+      const bool redo = (warp_ovf | xflag[(par * 4 + q) * 2 + (hf ^ 1)]) != 0;
+      if (redo) {
+        // exact path: new max >= every logit of this tile; rescale history, recompute P from the registers
+        const float m_new = fmaxf(m, tmax_row);
+        if (j > 0) {
+          const float alpha = ex2_approx(m - m_new);  // m is finite for j > 0
+          if (__any_sync(0xffffffffu, alpha != 1.f)) rescale_o(alpha);
+          l *= alpha;
         }
-        float p[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float e = ex2_approx(fmaf(__uint_as_float(v[i]), a.scale_log2, -m));
-          if (valid != BLOCK_KV && c * 32 + i >= valid) e = 0.f;
-          p[i] = e;
-          l += e;
-        }
-        uint32_t pk[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(p[2 * i], p[2 * i + 1]);
-        tmem_st16(p_tmem + c * 16, pk);
+        m = m_new;
+        const uint64_t nm2 = pack2(-m, -m);
+        lsum[0] = 0ull;
+        lsum[1] = 0ull;
+        if (full) { exp32<false>(sv, sc2, nm2, lsum, p_tmem, 32); exp32<false>(sv + 32, sc2, nm2, lsum, p_tmem + 16, 32); }
+        else { exp32<true>(sv, sc2, nm2, lsum, p_tmem, vcols); exp32<true>(sv + 32, sc2, nm2, lsum, p_tmem + 16, vcols - 32); }
+      } else if (tmax_row > m + 8.f) {
+        // lazy rescale: this tile used the old max; fold the change into O and l before the next tile
+        alpha_pend = ex2_approx(m - tmax_row);
+        m = tmax_row;
+      }
+      {
+        float s0, s1, s2, s3;
+        unpack2(lsum[0], s0, s1);
+        unpack2(lsum[1], s2, s3);
+        l += (s0 + s1) + (s2 + s3);
       }
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_ready);
     }
-    // ---- epilogue: O / l -> bf16 -> global ----
+    // ---- epilogue: O / l -> bf16 -> global (a pending rescale multiplies O and l alike: skipped) ----
     mbar_wait(pv_done, (n_tiles - 1) & 1);
     tc_fence_after();
-    const float inv_l = 1.0f / l;
-    bf16* orow = a.out + static_cast<size_t>(row0 + qrow) * a.ld_out + col0;
+    xsum[r * 2 + hf] = l;
+    pair_barrier(q);
+    const float inv_l = 1.0f / (l + xsum[r * 2 + (hf ^ 1)]);
+    bf16* orow = a.out + static_cast<size_t>(q_row0 + qrow) * a.ld_out + col0 + hf * (C::D / 2);
 #pragma unroll 1
-    for (int c = 0; c < C::D / 16; ++c) {
+    for (int c = 0; c < C::D / 2; c += 16) {
       uint32_t v[16];
-      tmem_ld16(o_tmem + c * 16, v);
+      tmem_ld16(o_tmem + c, v);
       tmem_ld_wait();
-      if (qrow < a.seq) {
+      if (qrow < a.seq_q) {
         uint4 o0, o1;
         o0.x = pack_bf16x2(__uint_as_float(v[0]) * inv_l, __uint_as_float(v[1]) * inv_l);
         o0.y = pack_bf16x2(__uint_as_float(v[2]) * inv_l, __uint_as_float(v[3]) * inv_l);
@@ -280,7 +386,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         o1.y = pack_bf16x2(__uint_as_float(v[10]) * inv_l, __uint_as_float(v[11]) * inv_l);
         o1.z = pack_bf16x2(__uint_as_float(v[12]) * inv_l, __uint_as_float(v[13]) * inv_l);
         o1.w = pack_bf16x2(__uint_as_float(v[14]) * inv_l, __uint_as_float(v[15]) * inv_l);
-        uint4* op = reinterpret_cast<uint4*>(orow + c * 16);
+        uint4* op = reinterpret_cast<uint4*>(orow + c);
         op[0] = o0;
         op[1] = o1;
       }
@@ -289,7 +395,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == 9) {
     tc_fence_after();
     tmem_dealloc(tmem, C::TMEM_COLS);
   }
@@ -301,9 +407,10 @@ int launch_attn(const AttnLaunch& L, cudaStream_t stream) {
   static bool attr_set[64] = {};
   if (int rc = ensure_dyn_smem(attn_fwd_kernel<NB>, C::SMEM_BYTES, attr_set)) return rc;
   AttKernelArgs a;
-  a.seq = L.d.seq;
+  a.seq_q = L.d.seq;
+  a.seq_kv = L.d.seq_kv > 0 ? L.d.seq_kv : L.d.seq;
   a.heads = L.d.heads;
-  a.n_kv_tiles = (L.d.seq + BLOCK_KV - 1) / BLOCK_KV;
+  a.n_kv_tiles = (a.seq_kv + BLOCK_KV - 1) / BLOCK_KV;
   a.scale_log2 = L.d.scale * 1.4426950408889634f;
   a.out = L.d.out;
   a.ld_out = L.d.ld_out;
@@ -318,16 +425,19 @@ int launch_attn(const AttnLaunch& L, cudaStream_t stream) {
 int attn_prepare(const AttnDesc& d, AttnLaunch* L) {
   D4D_REQUIRE(d.head_dim == 64 || d.head_dim == 128 || d.head_dim == 192,
               "attention head_dim (after padding) must be 64, 128 or 192");
-  D4D_REQUIRE(d.batch > 0 && d.seq > 0 && d.heads > 0, "empty attention problem");
-  D4D_REQUIRE(d.ld_qkv % 8 == 0 && d.ld_out % 8 == 0, "leading dimensions must be multiples of 8");
+  D4D_REQUIRE(d.batch > 0 && d.seq > 0 && d.heads > 0 && d.seq_kv >= 0, "empty attention problem");
+  D4D_REQUIRE(d.ld_qkv % 8 == 0 && d.ld_out % 8 == 0 && d.ld_kv % 8 == 0, "leading dimensions must be multiples of 8");
   D4D_REQUIRE(d.scale > 0.f, "softmax scale must be positive");
   L->d = d;
   L->variant = d.head_dim / 64;
-  const uint64_t tokens = static_cast<uint64_t>(d.batch) * d.seq;
+  const int seq_kv = d.seq_kv > 0 ? d.seq_kv : d.seq;
+  const int ld_kv = d.ld_kv > 0 ? d.ld_kv : d.ld_qkv;
+  const uint64_t q_tokens = static_cast<uint64_t>(d.batch) * d.seq;
+  const uint64_t kv_tokens = static_cast<uint64_t>(d.batch) * seq_kv;
   const uint64_t width = static_cast<uint64_t>(d.heads) * d.head_dim;
-  if (int rc = make_tmap_2d(&L->tmap_q, d.q, tokens, width, d.ld_qkv, 64, BLOCK_Q, 128)) return rc;
-  if (int rc = make_tmap_2d(&L->tmap_k, d.k, tokens, width, d.ld_qkv, 64, BLOCK_KV, 128)) return rc;
-  if (int rc = make_tmap_2d(&L->tmap_v, d.v, tokens, width, d.ld_qkv, 64, BLOCK_KV, 128)) return rc;
+  if (int rc = make_tmap_2d(&L->tmap_q, d.q, q_tokens, width, d.ld_qkv, 64, BLOCK_Q, 128)) return rc;
+  if (int rc = make_tmap_2d(&L->tmap_k, d.k, kv_tokens, width, ld_kv, 64, BLOCK_KV, 128)) return rc;
+  if (int rc = make_tmap_2d(&L->tmap_v, d.v, kv_tokens, width, ld_kv, 64, BLOCK_KV, 128)) return rc;
   L->grid_x = (d.seq + BLOCK_Q - 1) / BLOCK_Q;
   L->grid_y = d.batch * d.heads;
   D4D_REQUIRE(L->grid_y <= 65535, "batch*heads exceeds grid.y limit");
@@ -345,7 +455,8 @@ int attn_run(const AttnLaunch& L, cudaStream_t stream) {
 }
 
 double attn_flops(const AttnDesc& d) {
-  return 4.0 * d.batch * d.heads * static_cast<double>(d.seq) * d.seq * d.head_dim;
+  const double skv = d.seq_kv > 0 ? d.seq_kv : d.seq;
+  return 4.0 * d.batch * d.heads * static_cast<double>(d.seq) * skv * d.head_dim;
 }
 
 }  // namespace d4d

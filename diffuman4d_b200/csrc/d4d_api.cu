@@ -49,6 +49,7 @@ float* gn_scratch(size_t floats) {
     p = nullptr;
     cap = 0;
     if (cudaMalloc(&p, floats * sizeof(float)) != cudaSuccess) return nullptr;
+    if (cudaMemset(p, 0, floats * sizeof(float)) != cudaSuccess) return nullptr;
     cap = floats;
   }
   return p;
@@ -275,11 +276,14 @@ int d4d_op_groupnorm(const void* x1, int C1, const void* x2, int C2, int n_img, 
                      const float* gamma, const float* beta, int silu, void* out, void* stream) {
   D4D_API_BEGIN
   D4D_REQUIRE(n_img > 0 && hw > 0 && groups > 0, "empty GroupNorm");
-  float* part = gn_scratch(static_cast<size_t>(n_img) * 32 * groups * 2);
+  float* part = gn_scratch(d4d::groupnorm_scratch_floats(n_img, groups));
   if (!part) {
     d4d::set_error("GroupNorm scratch allocation failed");
     return 2;
   }
+  // the arrival counters live behind the (n_img-dependent) partial/final regions: zero them for this shape
+  const size_t ctr_off = static_cast<size_t>(n_img) * 32 * groups * 2 + static_cast<size_t>(n_img) * groups * 2;
+  D4D_CUDA_OK(cudaMemsetAsync(part + ctr_off, 0, sizeof(unsigned int) * n_img, static_cast<cudaStream_t>(stream)));
   return d4d::groupnorm_run(static_cast<const bf16*>(x1), C1, static_cast<const bf16*>(x2), C2, n_img, hw, groups, eps,
                             gamma, beta, silu, static_cast<bf16*>(out), part, static_cast<cudaStream_t>(stream));
   D4D_API_END

@@ -31,7 +31,7 @@ constexpr int STAGES = 4;
 constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;     // 16 KB
 constexpr int B_BYTES_MAX = 256 * BLOCK_K * 2;     // 32 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES_MAX; // 48 KB
-constexpr int NUM_THREADS = 192;                   // warp0 TMA, warp1 MMA(+TMEM alloc), warps2-5 epilogue
+constexpr int NUM_THREADS = 320;                   // warp0 TMA, warp1 MMA(+TMEM alloc), warps2-9 epilogue
 constexpr int TMEM_COLS = 512;
 constexpr int ACC_STRIDE = 256;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
@@ -55,6 +55,14 @@ __device__ __forceinline__ void tile_coords(const GemmKernelArgs& a, int m_tile,
     t.y0 = ty * a.BH;
     t.n_img0 = tn * a.BN;
   }
+}
+
+__device__ __forceinline__ void add8_bf16(float* f, const uint4& u) {
+  float2 p;
+  p = unpack_bf16x2(u.x); f[0] += p.x; f[1] += p.y;
+  p = unpack_bf16x2(u.y); f[2] += p.x; f[3] += p.y;
+  p = unpack_bf16x2(u.z); f[4] += p.x; f[5] += p.y;
+  p = unpack_bf16x2(u.w); f[6] += p.x; f[7] += p.y;
 }
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -85,7 +93,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 4);
+      mbar_init(&tempty[i], 8);
     }
     fence_mbar_init();
   }
@@ -159,8 +167,9 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       __syncwarp();
     }
   } else {
-    // ===================== epilogue (warps 2..5 -> TMEM lane quarter warp%4) =====================
+    // ===== epilogue: warps 2..9; TMEM lane quarter = warp%4, the two warps of a quarter take alternate 16-col chunks =====
     const int q = warp & 3;
+    const int chunk0 = (warp - 2) >> 2;
     const int r = q * 32 + lane;  // row within the 128-row tile
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -194,37 +203,57 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * ACC_STRIDE + (static_cast<uint32_t>(q * 32) << 16);
 
+      // Residual / row-vector loads of chunk c+2 are issued before the TMEM wait of chunk c so that their L2/HBM latency
+      // overlaps the TMEM load and the math of the current chunk; bias (L1-resident broadcast) is loaded under the wait.
       if (!a.geglu) {
         const int chunks = a.block_n / 16;
-        for (int c = 0; c < chunks; ++c) {
+        const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+        uint4 r0 = z4, r1 = z4, v0 = z4, v1 = z4, nr0 = z4, nr1 = z4, nv0 = z4, nv1 = z4;
+        const bf16* res_row = a.residual ? a.residual + static_cast<size_t>(row) * a.ld_res + n0 : nullptr;
+        const bf16* rv_row = a.rowvec ? a.rowvec + static_cast<size_t>(img) * a.ld_rowvec + n0 : nullptr;
+        const bool ld_res = valid && res_row != nullptr, ld_rv = valid && rv_row != nullptr;
+        if (chunk0 < chunks) {
+          if (ld_res) {  // plain loads: the residual may alias the output (in-place add)
+            r0 = *reinterpret_cast<const uint4*>(res_row + chunk0 * 16);
+            r1 = *reinterpret_cast<const uint4*>(res_row + chunk0 * 16 + 8);
+          }
+          if (ld_rv) {
+            v0 = __ldg(reinterpret_cast<const uint4*>(rv_row + chunk0 * 16));
+            v1 = __ldg(reinterpret_cast<const uint4*>(rv_row + chunk0 * 16 + 8));
+          }
+        }
+        for (int c = chunk0; c < chunks; c += 2) {
           uint32_t v[16];
           tmem_ld16(taddr + c * 16, v);
+          const int col = n0 + c * 16;
+          if (c + 2 < chunks) {
+            if (ld_res) {
+              nr0 = *reinterpret_cast<const uint4*>(res_row + (c + 2) * 16);
+              nr1 = *reinterpret_cast<const uint4*>(res_row + (c + 2) * 16 + 8);
+            }
+            if (ld_rv) {
+              nv0 = __ldg(reinterpret_cast<const uint4*>(rv_row + (c + 2) * 16));
+              nv1 = __ldg(reinterpret_cast<const uint4*>(rv_row + (c + 2) * 16 + 8));
+            }
+          }
+          float4 b4[4];
+          if (a.bias) {
+            const float4* bp = reinterpret_cast<const float4*>(a.bias + col);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) b4[i] = __ldg(bp + i);
+          }
           tmem_ld_wait();
           if (valid) {
-            const int col = n0 + c * 16;
             float f[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
             if (a.bias) {
-              const float4* bp = reinterpret_cast<const float4*>(a.bias + col);
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
-                float4 b = __ldg(bp + i);
-                f[4 * i] += b.x; f[4 * i + 1] += b.y; f[4 * i + 2] += b.z; f[4 * i + 3] += b.w;
+                f[4 * i] += b4[i].x; f[4 * i + 1] += b4[i].y; f[4 * i + 2] += b4[i].z; f[4 * i + 3] += b4[i].w;
               }
             }
-            if (a.rowvec) {
-              const uint4* rp = reinterpret_cast<const uint4*>(a.rowvec + static_cast<size_t>(img) * a.ld_rowvec + col);
-#pragma unroll
-              for (int i = 0; i < 2; ++i) {
-                uint4 u = __ldg(rp + i);
-                float2 p;
-                p = unpack_bf16x2(u.x); f[8 * i] += p.x; f[8 * i + 1] += p.y;
-                p = unpack_bf16x2(u.y); f[8 * i + 2] += p.x; f[8 * i + 3] += p.y;
-                p = unpack_bf16x2(u.z); f[8 * i + 4] += p.x; f[8 * i + 5] += p.y;
-                p = unpack_bf16x2(u.w); f[8 * i + 6] += p.x; f[8 * i + 7] += p.y;
-              }
-            }
+            if (a.rowvec) { add8_bf16(f, v0); add8_bf16(f + 8, v1); }
             if (a.act == 1) {
 #pragma unroll
               for (int i = 0; i < 16; ++i) f[i] = silu_f(f[i]);
@@ -233,18 +262,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
               for (int i = 0; i < 16; ++i) f[i] *= a.out_scale;
             }
-            if (a.residual) {
-              const uint4* rp = reinterpret_cast<const uint4*>(a.residual + static_cast<size_t>(row) * a.ld_res + col);
-#pragma unroll
-              for (int i = 0; i < 2; ++i) {
-                uint4 u = rp[i];
-                float2 p;
-                p = unpack_bf16x2(u.x); f[8 * i] += p.x; f[8 * i + 1] += p.y;
-                p = unpack_bf16x2(u.y); f[8 * i + 2] += p.x; f[8 * i + 3] += p.y;
-                p = unpack_bf16x2(u.z); f[8 * i + 4] += p.x; f[8 * i + 5] += p.y;
-                p = unpack_bf16x2(u.w); f[8 * i + 6] += p.x; f[8 * i + 7] += p.y;
-              }
-            }
+            if (a.residual) { add8_bf16(f, r0); add8_bf16(f + 8, r1); }
             uint4* op = reinterpret_cast<uint4*>(a.out + static_cast<size_t>(row) * a.ldo + col);
             uint4 o0, o1;
             o0.x = pack_bf16x2(f[0], f[1]);   o0.y = pack_bf16x2(f[2], f[3]);
@@ -254,32 +272,42 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             op[0] = o0;
             op[1] = o1;
           }
+          r0 = nr0; r1 = nr1; v0 = nv0; v1 = nv1;
         }
       } else {
         // GEGLU: this N tile holds [a (block_n/2 cols) | g (block_n/2 cols)] for output cols
         // n_tile*block_n/2 .. +block_n/2
         const int half = a.block_n / 2;
         const int chunks = half / 16;
-        for (int c = 0; c < chunks; ++c) {
+        for (int c = chunk0; c < chunks; c += 2) {
           uint32_t va[16], vg[16];
           tmem_ld16(taddr + c * 16, va);
           tmem_ld16(taddr + half + c * 16, vg);
+          float4 ba[4], bg[4];
+          if (a.bias) {
+            const float4* pa = reinterpret_cast<const float4*>(a.bias + n0 + c * 16);
+            const float4* pg = reinterpret_cast<const float4*>(a.bias + n0 + half + c * 16);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { ba[i] = __ldg(pa + i); bg[i] = __ldg(pg + i); }
+          }
           tmem_ld_wait();
           if (valid) {
-            const int wcol = n0 + c * 16;  // column in the (interleaved) weight/bias space
-            float fa[16], fg[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) { fa[i] = __uint_as_float(va[i]); fg[i] = __uint_as_float(vg[i]); }
-            if (a.bias) {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                fa[i] += __ldg(a.bias + wcol + i);
-                fg[i] += __ldg(a.bias + wcol + half + i);
-              }
-            }
             float o[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) o[i] = fa[i] * gelu_erf_f(fg[i]);
+            for (int i = 0; i < 4; ++i) {
+              float fa0 = __uint_as_float(va[4 * i]), fa1 = __uint_as_float(va[4 * i + 1]);
+              float fa2 = __uint_as_float(va[4 * i + 2]), fa3 = __uint_as_float(va[4 * i + 3]);
+              float fg0 = __uint_as_float(vg[4 * i]), fg1 = __uint_as_float(vg[4 * i + 1]);
+              float fg2 = __uint_as_float(vg[4 * i + 2]), fg3 = __uint_as_float(vg[4 * i + 3]);
+              if (a.bias) {
+                fa0 += ba[i].x; fa1 += ba[i].y; fa2 += ba[i].z; fa3 += ba[i].w;
+                fg0 += bg[i].x; fg1 += bg[i].y; fg2 += bg[i].z; fg3 += bg[i].w;
+              }
+              o[4 * i] = fa0 * gelu_erf_f(fg0);
+              o[4 * i + 1] = fa1 * gelu_erf_f(fg1);
+              o[4 * i + 2] = fa2 * gelu_erf_f(fg2);
+              o[4 * i + 3] = fa3 * gelu_erf_f(fg3);
+            }
             const int ocol = n_tile * half + c * 16;
             uint4* op = reinterpret_cast<uint4*>(a.out + static_cast<size_t>(row) * a.ldo + ocol);
             uint4 o0, o1;

@@ -80,6 +80,8 @@ struct AttnDesc {
   bf16* out = nullptr;  // [tokens, ld_out]
   int ld_out = 0;
   int batch = 0, seq = 0, heads = 0, head_dim = 0;
+  int seq_kv = 0;     // keys/values per batch entry (0 = seq); k/v rows of batch b start at b*seq_kv
+  int ld_kv = 0;      // leading dimension of the k/v matrix (0 = ld_qkv)
   float scale = 0.f;  // softmax scale (head_dim^-0.5)
 };
 struct AttnLaunch {
@@ -96,9 +98,12 @@ double attn_flops(const AttnDesc& d);
 // HBM-bound kernels (norm.cu, elementwise.cu)
 // --------------------------------------------------------------------------------------------
 // GroupNorm over NHWC tokens [n_img, hw, C1 (+C2)] (optional virtual channel concat of two sources),
-// fused affine + optional SiLU; writes bf16 [n_img*hw, C1+C2].  partials: fp32 scratch
-// [n_img * splits * groups * 3].
+// fused affine + optional SiLU; writes bf16 [n_img*hw, C1+C2].  scratch: groupnorm_scratch_floats(n_img, groups) floats,
+// zero-initialised once (slab partials | final mean/rstd | self-resetting arrival counters).
 int groupnorm_splits(int hw);
+inline size_t groupnorm_scratch_floats(int n_img, int groups) {
+  return static_cast<size_t>(n_img) * 32 * groups * 2 + static_cast<size_t>(n_img) * groups * 2 + n_img + 16;
+}
 int groupnorm_run(const bf16* x1, int C1, const bf16* x2, int C2, int n_img, int hw, int groups, float eps,
                   const float* gamma, const float* beta, int silu, bf16* out, float* partials, cudaStream_t stream);
 // LayerNorm over rows of width C (C % 8 == 0, C <= 2048)

@@ -29,6 +29,8 @@ struct GnArgs {
   int silu;
   bf16* out;
   float* partials;  // [n_img][splits][groups][2] = (mean, M2)
+  float* final_stats;   // [n_img][groups][2] = (mean, rstd), written by the last stats CTA of each image
+  unsigned int* counters;  // [n_img] arrival counters (self-resetting)
 };
 
 __device__ __forceinline__ uint4 gn_load(const GnArgs& a, int img, int pixel, int oct) {
@@ -63,7 +65,26 @@ __global__ void gn_stats_kernel(const GnArgs a) {
   if (npix > 0) {
     uint4 u0 = gn_load(a, img, p0, oct);
     unpack8(u0, piv);
-    for (int p = p0 + prow; p < p1; p += a.rows_per_iter) {
+    // 4 independent 16-byte loads in flight per thread (memory-level parallelism), then accumulate
+    const int stride = a.rows_per_iter;
+    int p = p0 + prow;
+    for (; p + 3 * stride < p1; p += 4 * stride) {
+      uint4 u[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) u[k] = gn_load(a, img, p + k * stride, oct);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float f[8];
+        unpack8(u[k], f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float d = f[i] - piv[i];
+          s[i] += d;
+          ss[i] = fmaf(d, d, ss[i]);
+        }
+      }
+    }
+    for (; p < p1; p += stride) {
       uint4 u = gn_load(a, img, p, oct);
       float f[8];
       unpack8(u, f);
@@ -119,12 +140,18 @@ __global__ void gn_stats_kernel(const GnArgs a) {
     dst[0] = mean;
     dst[1] = m2;
   }
-}
-
-// smem: g_mean[groups], g_rstd[groups]
-__global__ void gn_apply_kernel(const GnArgs a) {
-  extern __shared__ float sm[];
-  const int split = blockIdx.x, img = blockIdx.y;
+  // ---- the last CTA of this image merges the slabs once (instead of every apply-CTA re-merging them) ----
+  __shared__ unsigned int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int prev = atomicAdd(&a.counters[img], 1u);
+    s_last = (prev == static_cast<unsigned int>(a.splits - 1)) ? 1u : 0u;
+    if (s_last) a.counters[img] = 0u;  // reset for the next GroupNorm on this stream
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
   for (int g = threadIdx.x; g < a.groups; g += blockDim.x) {
     float mean = 0.f, m2 = 0.f, cnt = 0.f;
     for (int sp = 0; sp < a.splits; ++sp) {
@@ -133,16 +160,25 @@ __global__ void gn_apply_kernel(const GnArgs a) {
       const float nb = static_cast<float>(max(0, q1 - q0)) * a.cpg;
       if (nb <= 0.f) continue;
       const float* src = a.partials + ((static_cast<size_t>(img) * a.splits + sp) * a.groups + g) * 2;
-      const float mb = src[0], m2b = src[1];
+      const float mb = __ldcg(src), m2b = __ldcg(src + 1);
       const float tot = cnt + nb;
       const float delta = mb - mean;
       mean += delta * (nb / tot);
       m2 += m2b + delta * delta * (cnt * nb / tot);
       cnt = tot;
     }
-    sm[g] = mean;
-    sm[a.groups + g] = rsqrtf(m2 / cnt + a.eps);
+    float* dst = a.final_stats + (static_cast<size_t>(img) * a.groups + g) * 2;
+    dst[0] = mean;
+    dst[1] = rsqrtf(m2 / cnt + a.eps);
   }
+}
+
+// smem: g_mean[groups], g_rstd[groups]
+__global__ void gn_apply_kernel(const GnArgs a) {
+  extern __shared__ float sm[];
+  const int split = blockIdx.x, img = blockIdx.y;
+  for (int g = threadIdx.x; g < 2 * a.groups; g += blockDim.x)
+    sm[(g & 1) * a.groups + (g >> 1)] = a.final_stats[static_cast<size_t>(img) * a.groups * 2 + g];
   __syncthreads();
   const int oct = threadIdx.x % a.n_oct;
   const int prow = threadIdx.x / a.n_oct;
@@ -157,8 +193,7 @@ __global__ void gn_apply_kernel(const GnArgs a) {
   }
   const int p0 = split * a.pps;
   const int p1 = min(a.hw, p0 + a.pps);
-  for (int p = p0 + prow; p < p1; p += a.rows_per_iter) {
-    uint4 u = gn_load(a, img, p, oct);
+  auto apply_one = [&](const uint4& u, int p) {
     float f[8];
     unpack8(u, f);
 #pragma unroll
@@ -173,7 +208,17 @@ __global__ void gn_apply_kernel(const GnArgs a) {
     o.w = pack_bf16x2(f[6], f[7]);
     const size_t tok = static_cast<size_t>(img) * a.hw + p;
     *reinterpret_cast<uint4*>(a.out + tok * a.C + oct * 8) = o;
+  };
+  const int stride = a.rows_per_iter;
+  int p = p0 + prow;
+  for (; p + 3 * stride < p1; p += 4 * stride) {
+    uint4 u[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) u[k] = gn_load(a, img, p + k * stride, oct);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) apply_one(u[k], p + k * stride);
   }
+  for (; p < p1; p += stride) apply_one(gn_load(a, img, p, oct), p);
 }
 
 // one warp per row; the row lives in registers (<= 8 x 16-byte chunks per lane => C <= 2048)
@@ -275,6 +320,9 @@ int groupnorm_run(const bf16* x1, int C1, const bf16* x2, int C2, int n_img, int
   a.cpg = C / groups;
   a.eps = eps;
   a.gamma = gamma; a.beta = beta; a.silu = silu; a.out = out; a.partials = partials;
+  // scratch layout: partials | final stats | counters (counters must be zero before first use; they self-reset)
+  a.final_stats = partials + static_cast<size_t>(n_img) * 32 * groups * 2;
+  a.counters = reinterpret_cast<unsigned int*>(a.final_stats + static_cast<size_t>(n_img) * groups * 2);
   const int threads = a.n_oct * a.rows_per_iter;
   dim3 grid(a.splits, n_img);
   const size_t smem_stats = sizeof(float) * (2 * C + 2 * static_cast<size_t>(a.rows_per_iter) * C);

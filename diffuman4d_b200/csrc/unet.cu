@@ -679,7 +679,11 @@ class PlanBuilder {
     const int C0 = ch[0], TE = 4 * C0, L = cfg.layers_per_block;
     const int M0 = B * h * w;
 
-    gn_partials_ = reinterpret_cast<float*>(alloc(static_cast<size_t>(B) * 32 * cfg.norm_num_groups * 2 * 2));
+    {
+      const size_t fl = groupnorm_scratch_floats(B, cfg.norm_num_groups);
+      gn_partials_ = reinterpret_cast<float*>(alloc(fl * 2));
+      if (!dry_ && cudaMemset(gn_partials_, 0, fl * sizeof(float)) != cudaSuccess) rc_ = 2;
+    }
 
     // ---- 1. time (+ frame-index) embedding: UNET:519-546 ----
     bf16* tsin = alloc(static_cast<size_t>(B) * C0);

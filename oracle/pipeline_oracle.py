@@ -66,6 +66,29 @@ class DDIMOracle:
         a_t = self.alphas_cumprod[timestep]
         a_prev = self.alphas_cumprod[prev_t] if prev_t >= 0 else self.final_alpha_cumprod
         b_t = 1 - a_t
+        if sample.dtype == torch.bfloat16:
+            # The reference runs this on CUDA bf16 tensors with 0-dim fp32 CPU coefficients: TensorIterator keeps such
+            # "cpu scalar" operands in fp32 (opmath) and rounds every op's result to bf16.  Restated explicitly so the
+            # emulation does not depend on which CPU kernel torch happens to pick for mixed bf16/fp32 operands.
+            r = lambda x: x.to(torch.bfloat16).float()
+            x, e = sample.float(), model_output.float()
+            sa, sb = float(a_t ** 0.5), float(b_t ** 0.5)
+            sap, sd = float(a_prev ** 0.5), float((1 - a_prev) ** 0.5)
+            f32 = lambda v: torch.tensor(v, dtype=torch.float32)
+            if cfg.prediction_type == "epsilon":
+                x0 = r(r(x - r(f32(sb) * e)) / f32(sa))
+                eps = e
+            elif cfg.prediction_type == "v_prediction":
+                x0 = r(r(f32(sa) * x) - r(f32(sb) * e))
+                eps = r(r(f32(sa) * e) + r(f32(sb) * x))
+            elif cfg.prediction_type == "sample":
+                x0 = e
+                eps = r(r(x - r(f32(sa) * x0)) / f32(sb))
+            else:
+                raise ValueError(cfg.prediction_type)
+            if cfg.clip_sample:
+                x0 = x0.clamp(-cfg.clip_sample_range, cfg.clip_sample_range)
+            return r(r(f32(sap) * x0) + r(f32(sd) * eps)).to(torch.bfloat16)
         if cfg.prediction_type == "epsilon":
             x0 = (sample - b_t ** 0.5 * model_output) / a_t ** 0.5
             eps = model_output
@@ -141,7 +164,11 @@ def denoise_window_oracle(unet: Callable, sched: DDIMOracle, *, latents, pixel_l
         noise = unet(x, t_in, skel, domains, F_)
         if cfg_on:                                         # PIPE:408-410
             u, c = noise.chunk(2)
-            noise = u + guidance_scale * (c - u)
+            if noise.dtype == torch.bfloat16:      # CUDA bf16 semantics: fp32 opmath, one rounding per op
+                r = lambda x: x.to(torch.bfloat16).float()
+                noise = r(u.float() + r(guidance_scale * r(c.float() - u.float()))).to(torch.bfloat16)
+            else:
+                noise = u + guidance_scale * (c - u)
         new = []
         for j in range(F_):                                # PIPE:413-422
             lat = latents[j:j + 1]

@@ -158,7 +158,7 @@ def test_cfg_ddim_step(cuda, pred):
         # oracle: CFG combine + per-frame step, in bf16 (the reference's arithmetic) or fp32
         dt = torch.bfloat16 if emulate else torch.float32
         u, c = noise.to(dt).chunk(2)
-        eps = u + 2.0 * (c - u)
+        eps = u + 2.0 * (c - u)          # 2.0 and the differences are exact roundings in either dtype
         ref = []
         for j in range(F):
             if mask[j, 0, 0, 0] == 0:
