@@ -7,18 +7,19 @@
 // and attn2 (per-image).  Q/K/V are read in place from the fused QKV-GEMM output [tokens, 3C] through
 // strided TMA boxes, so "(b t) hw c -> b (t hw) c" and the head split are address arithmetic only.
 //
-// One CTA = 128 query rows of one (batch, head); two CTAs are co-resident per SM at head_dim 64.
-// Warp roles (320 threads):
-//   warps 0-7  softmax.  TMEM lane quarter = warp%4 (row = lane), column half = warp/4: the two warps of a row
-//              quarter split the 128 key columns of S, the 64 packed P columns and the D columns of O.
-//              Each thread pulls its 64 S values into registers with ONE exposed TMEM round trip per tile and
-//              releases S at once (Q.K(j+1) runs under the exp phase).  P = exp2(S*scale - m) is computed with the
+// One CTA = 128 query rows of one (batch, head), K/V tiles of 64 keys; two CTAs are co-resident per SM at head_dim 64
+// (256 TMEM columns each: S0 S1 | P0 P1 | O).  S and P are DOUBLE-BUFFERED in TMEM so that the three stages
+//     S(j+2) = Q K^T   |   softmax(j): S -> P   |   O += P(j-1) V
+// run concurrently and the softmax warps never wait for the tensor core in steady state.
+// Warp roles (192 threads):
+//   warps 0-3  softmax: thread t owns query row t (TMEM lane t).  The 64 S values of the tile are pulled into
+//              registers with one exposed TMEM round trip and S is released at once.  P = exp2(S*scale - m) uses the
 //              running max m of the previous tiles; if the row max grows by more than 8 (log2 units) O and l are
-//              rescaled before the next tile, and only if it would overflow (> 100, always for tile 0) P is
-//              recomputed from the registers with the new max.  Row sums are kept per thread and combined once at
-//              the end.  FMNMX3 / FFMA2 / FADD2 packed math; the masked tail tile is a separate instantiation.
-//   warp  8    TMA producer: Q once, then K_0, K_1, V_0, K_2, V_1, ... through a ring of 16 KB*NB slots
-//   warp  9    MMA issuer:   S = Q K_j^T (SS, both K-major), O += P V_j (A = P bf16 from TMEM, B = V MN-major)
+//              rescaled before the next tile, and only if it would overflow (> 100; always for tile 0) P is recomputed
+//              from the registers with the new max.  FMNMX3 / FFMA2 / FADD2 packed math; the masked tail tile is a
+//              separate instantiation.
+//   warp  4    TMA producer: Q once, then K0 K1 K2 V0 K3 V1 ... through a ring of 8 KB*NB slots
+//   warp  5    MMA issuer:   S = Q K_j^T (SS, both K-major), O += P V_j (A = P bf16 from TMEM, B = V MN-major)
 #include <math.h>
 
 #include "kernels.h"
@@ -28,20 +29,20 @@ namespace d4d {
 namespace {
 
 constexpr int BLOCK_Q = 128;
-constexpr int BLOCK_KV = 128;
-constexpr int ATT_THREADS = 320;
-constexpr int TILE_BYTES = 128 * 64 * 2;  // one [128 rows][64 ch] swizzled box
+constexpr int BLOCK_KV = 64;
+constexpr int ATT_THREADS = 192;
+constexpr int QTILE_BYTES = 128 * 64 * 2;  // one [128 rows][64 ch] swizzled box
+constexpr int KTILE_BYTES = 64 * 64 * 2;   // one [64 keys][64 ch] swizzled box
 
 template <int NB>
 struct AttCfg {
   static constexpr int D = 64 * NB;
-  static constexpr int SLOT_BYTES = TILE_BYTES * NB;  // one K or V tile
-  static constexpr int SLOTS = NB == 3 ? 3 : 5;
-  static constexpr int Q_BYTES = TILE_BYTES * NB;
-  static constexpr int XCH_BYTES = 128 * 2 * 4 * 2 + 128 * 2 * 4 + 128;  // tile-max exchange (2 parities) + row sums + redo flags
-  static constexpr int SMEM_BYTES = Q_BYTES + SLOTS * SLOT_BYTES + 1024 + 256 + XCH_BYTES;
+  static constexpr int SLOT_BYTES = KTILE_BYTES * NB;  // one K or V tile
+  static constexpr int SLOTS = NB == 1 ? 8 : 6;
+  static constexpr int Q_BYTES = QTILE_BYTES * NB;
+  static constexpr int SMEM_BYTES = Q_BYTES + SLOTS * SLOT_BYTES + 1024 + 256;
   static constexpr int TMEM_COLS = NB == 1 ? 256 : 512;
-  static constexpr int COL_S = 0, COL_P = 128, COL_O = 192;
+  static constexpr int COL_S = 0, COL_P = 128, COL_O = 192;  // S0 S1 (64 each) | P0 P1 (32 each) | O (D)
 };
 
 struct AttKernelArgs {
@@ -84,9 +85,6 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8])
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]),
                "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
                : "memory");
-}
-__device__ __forceinline__ void pair_barrier(int q) {  // the two warps (64 threads) that share a TMEM lane quarter
-  asm volatile("bar.sync %0, 64;" ::"r"(q + 1) : "memory");
 }
 
 // Row max over 32 S columns held in registers (four independent FMNMX3 chains); kMasked: only columns < valid count
@@ -144,14 +142,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   uint64_t* ring_full = bars;              // [SLOTS]
   uint64_t* ring_empty = bars + C::SLOTS;  // [SLOTS]
   uint64_t* q_full = bars + 2 * C::SLOTS;
-  uint64_t* s_full = q_full + 1;
-  uint64_t* s_free = q_full + 2;
-  uint64_t* p_ready = q_full + 3;
-  uint64_t* pv_done = q_full + 4;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_full + 5);
-  float* xmax = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);  // [2 parity][128 rows][2 halves]
-  float* xsum = xmax + 2 * 128 * 2;                                                  // [128 rows][2 halves]
-  int* xflag = reinterpret_cast<int*>(xsum + 128 * 2);                               // [2 parity][4 quarters][2 halves]
+  uint64_t* s_full = q_full + 1;   // [2]
+  uint64_t* s_free = q_full + 3;   // [2]
+  uint64_t* p_ready = q_full + 5;  // [2]
+  uint64_t* pv_done = q_full + 7;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_full + 9);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -170,19 +165,21 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       mbar_init(&ring_empty[i], 1);
     }
     mbar_init(q_full, 1);
-    mbar_init(s_full, 1);
-    mbar_init(s_free, 8);
-    mbar_init(p_ready, 8);
-    mbar_init(pv_done, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_free[i], 4);
+      mbar_init(&p_ready[i], 4);
+      mbar_init(&pv_done[i], 1);
+    }
     fence_mbar_init();
   }
-  if (warp == 9) tmem_alloc(tmem_slot, C::TMEM_COLS);
+  if (warp == 5) tmem_alloc(tmem_slot, C::TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == 8) {
+  if (warp == 4) {
     // ============================ TMA producer ============================
     if (lane == 0) {
       tma_prefetch_desc(&tmap_q);
@@ -191,98 +188,99 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       mbar_expect_tx(q_full, C::Q_BYTES);
 #pragma unroll
       for (int nb = 0; nb < NB; ++nb)
-        tma_load_2d(sQ + nb * TILE_BYTES, &tmap_q, q_full, col0 + nb * 64, q_row0 + q_tile * BLOCK_Q);
+        tma_load_2d(sQ + nb * QTILE_BYTES, &tmap_q, q_full, col0 + nb * 64, q_row0 + q_tile * BLOCK_Q);
       int slot = 0;
       uint32_t phase = 0;
-      // order of tiles through the ring: K0, K1, V0, K2, V1, ..., K(n-1), V(n-2), V(n-1)
-      for (int step = 0; step < 2 * n_tiles; ++step) {
-        int is_v, j;
-        if (step == 0) { is_v = 0; j = 0; }
-        else if (step == 2 * n_tiles - 1) { is_v = 1; j = n_tiles - 1; }
-        else { is_v = (step & 1) ? 0 : 1; j = is_v ? (step / 2 - 1) : ((step + 1) / 2); }
+      auto load_tile = [&](bool is_v, int j) {
         mbar_wait(&ring_empty[slot], phase ^ 1);
         uint8_t* dst = sRing + slot * C::SLOT_BYTES;
         mbar_expect_tx(&ring_full[slot], C::SLOT_BYTES);
 #pragma unroll
         for (int nb = 0; nb < NB; ++nb)
-          tma_load_2d(dst + nb * TILE_BYTES, is_v ? &tmap_v : &tmap_k, &ring_full[slot], col0 + nb * 64,
+          tma_load_2d(dst + nb * KTILE_BYTES, is_v ? &tmap_v : &tmap_k, &ring_full[slot], col0 + nb * 64,
                       kv_row0 + j * BLOCK_KV);
         if (++slot == C::SLOTS) { slot = 0; phase ^= 1; }
+      };
+      // same order as the MMA warp consumes: K0 K1, then for every j: K(j+2), V(j)
+      load_tile(false, 0);
+      if (n_tiles > 1) load_tile(false, 1);
+      for (int j = 0; j < n_tiles; ++j) {
+        if (j + 2 < n_tiles) load_tile(false, j + 2);
+        load_tile(true, j);
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == 5) {
     // ============================ MMA issuer ============================
     if (lane == 0) {
       const uint32_t idesc_qk = make_idesc_bf16(BLOCK_Q, BLOCK_KV, 0, 0);
       const uint32_t idesc_pv = make_idesc_bf16(BLOCK_Q, C::D, 0, 1);
-      const uint32_t s_tmem = tmem + C::COL_S, p_tmem = tmem + C::COL_P, o_tmem = tmem + C::COL_O;
+      const uint32_t o_tmem = tmem + C::COL_O;
       int slot = 0;
       uint32_t phase = 0;
-      auto issue_qk = [&]() {
+      auto issue_qk = [&](int j) {  // S[j&1] = Q K_j^T
         mbar_wait(&ring_full[slot], phase);
         tc_fence_after();
         const uint32_t kaddr = smem_u32(sRing + slot * C::SLOT_BYTES);
+        const uint32_t s_tmem = tmem + C::COL_S + (j & 1) * 64;
 #pragma unroll
         for (int nb = 0; nb < NB; ++nb) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const uint64_t ad = make_smem_desc(smem_u32(sQ) + nb * TILE_BYTES + k * 32, 0, 1024, 2);
-            const uint64_t bd = make_smem_desc(kaddr + nb * TILE_BYTES + k * 32, 0, 1024, 2);
+            const uint64_t ad = make_smem_desc(smem_u32(sQ) + nb * QTILE_BYTES + k * 32, 0, 1024, 2);
+            const uint64_t bd = make_smem_desc(kaddr + nb * KTILE_BYTES + k * 32, 0, 1024, 2);
             umma_ss(s_tmem, ad, bd, idesc_qk, (nb | k) != 0 ? 1u : 0u);
           }
         }
         umma_commit(&ring_empty[slot]);
-        umma_commit(s_full);
+        umma_commit(&s_full[j & 1]);
         if (++slot == C::SLOTS) { slot = 0; phase ^= 1; }
       };
-      auto issue_pv = [&](int j) {
+      auto issue_pv = [&](int j) {  // O += P[j&1] V_j
         mbar_wait(&ring_full[slot], phase);
         tc_fence_after();
         const uint32_t vaddr = smem_u32(sRing + slot * C::SLOT_BYTES);
+        const uint32_t p_tmem = tmem + C::COL_P + (j & 1) * 32;
 #pragma unroll
         for (int k = 0; k < BLOCK_KV / 16; ++k) {
-          // V tile = NB boxes of [128 keys][64 d] (d contiguous): MN-major B operand.
+          // V tile = NB boxes of [64 keys][64 d] (d contiguous): MN-major B operand.
           // 16 keys = two 8-row swizzle atoms = 2048 bytes; SBO = 1024 (next 8 keys), LBO = next 64-wide d block
-          const uint64_t bd = make_smem_desc(vaddr + k * 2048, TILE_BYTES, 1024, 2);
+          const uint64_t bd = make_smem_desc(vaddr + k * 2048, KTILE_BYTES, 1024, 2);
           umma_ts(o_tmem, p_tmem + k * 8, bd, idesc_pv, (j | k) != 0 ? 1u : 0u);
         }
         umma_commit(&ring_empty[slot]);
-        umma_commit(pv_done);
+        umma_commit(&pv_done[j & 1]);
         if (++slot == C::SLOTS) { slot = 0; phase ^= 1; }
       };
       mbar_wait(q_full, 0);
       tc_fence_after();
-      issue_qk();  // S(0)
+      issue_qk(0);
+      if (n_tiles > 1) issue_qk(1);
       for (int j = 0; j < n_tiles; ++j) {
-        if (j + 1 < n_tiles) {
-          mbar_wait(s_free, j & 1);  // every softmax thread holds its part of S(j) in registers
+        const uint32_t par = (j >> 1) & 1;
+        if (j + 2 < n_tiles) {
+          mbar_wait(&s_free[j & 1], par);  // every softmax thread holds S(j) in registers
           tc_fence_after();
-          issue_qk();                // S(j+1) runs under the exp phase of tile j
+          issue_qk(j + 2);
         }
-        mbar_wait(p_ready, j & 1);
+        mbar_wait(&p_ready[j & 1], par);
         tc_fence_after();
         issue_pv(j);
       }
     }
   } else {
     // ============================ softmax / correction / epilogue ============================
-    const int q = warp & 3;   // TMEM lane quarter
-    const int hf = warp >> 2;  // column half
-    const int r = q * 32 + lane;
-    const uint32_t lane_sel = static_cast<uint32_t>(q * 32) << 16;
-    const uint32_t s_tmem = tmem + C::COL_S + lane_sel + hf * 64;
-    const uint32_t p_tmem = tmem + C::COL_P + lane_sel + hf * 32;
-    const uint32_t o_tmem = tmem + C::COL_O + lane_sel + hf * (C::D / 2);
+    const int r = warp * 32 + lane;  // query row of this thread = TMEM lane
+    const uint32_t lane_sel = static_cast<uint32_t>(warp * 32) << 16;
+    const uint32_t o_tmem = tmem + C::COL_O + lane_sel;
     const int qrow = q_tile * BLOCK_Q + r;  // row within the sequence
     const uint64_t sc2 = pack2(a.scale_log2, a.scale_log2);
-    float m = -INFINITY;      // max used for the exponentials of the NEXT tile (scaled log2 units)
-    float l = 0.f;            // this thread's share of the row sum (its 64 columns of every tile)
-    float alpha_pend = 1.f;   // pending rescale of O and l (applied once P.V of the previous tile has landed)
+    float m = -INFINITY;     // running max (scaled log2 units) used for the exponentials of the next tile
+    float l = 0.f;           // running row sum
+    float alpha_pend = 1.f;  // pending rescale of O and l (applied once P.V of the previous tile has landed)
 
-    // O[:, my half] *= alpha (warp-collective; alpha is per lane/row)
-    auto rescale_o = [&](float alpha) {
+    auto rescale_o = [&](float alpha) {  // O[row, :] *= alpha (warp-collective; alpha is per lane/row)
 #pragma unroll 1
-      for (int c = 0; c < C::D / 2; c += 16) {
+      for (int c = 0; c < C::D; c += 16) {
         uint32_t v[16];
         tmem_ld16(o_tmem + c, v);
         tmem_ld_wait();
@@ -291,55 +289,58 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         tmem_st16(o_tmem + c, v);
       }
     };
+
     for (int j = 0; j < n_tiles; ++j) {
       const int valid = min(BLOCK_KV, a.seq_kv - j * BLOCK_KV);
-      const int vcols = valid - hf * 64;  // valid columns inside my half (<= 0 .. >= 64)
       const bool full = valid == BLOCK_KV;
-      const int par = j & 1;
-      mbar_wait(s_full, par);
+      const int buf = j & 1;
+      const uint32_t par = (j >> 1) & 1;
+      const uint32_t s_tmem = tmem + C::COL_S + buf * 64 + lane_sel;
+      const uint32_t p_tmem = tmem + C::COL_P + buf * 32 + lane_sel;
+      mbar_wait(&s_full[buf], par);
       tc_fence_after();
-      // my 64 columns of S(j) -> registers (one exposed TMEM latency per tile), then release S for Q.K(j+1)
+      // S(j) -> registers (one exposed TMEM latency per tile), then release the buffer for Q.K(j+2)
       uint32_t sv[64];
       tmem_ld32(s_tmem, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
       tmem_ld32(s_tmem + 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[32]));
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(s_free);
+      if (lane == 0) mbar_arrive(&s_free[buf]);
 
       float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
       if (full) { max32<false>(sv, mx, 32); max32<false>(sv + 32, mx, 32); }
-      else { max32<true>(sv, mx, vcols); max32<true>(sv + 32, mx, vcols - 32); }
+      else { max32<true>(sv, mx, valid); max32<true>(sv + 32, mx, valid - 32); }
       const float tmax = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * a.scale_log2;
 
-      if (j > 0) {  // P and O may only be touched once P.V(j-1) has landed
-        mbar_wait(pv_done, (j - 1) & 1);
+      if (__any_sync(0xffffffffu, alpha_pend != 1.f)) {  // rescale decided at the end of tile j-1
+        mbar_wait(&pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1);  // O holds P.V(0..j-1)
         tc_fence_after();
-        if (__any_sync(0xffffffffu, alpha_pend != 1.f)) {  // rescale decided at the end of the previous tile
-          rescale_o(alpha_pend);
-          l *= alpha_pend;
-          alpha_pend = 1.f;
-        }
+        rescale_o(alpha_pend);
+        l *= alpha_pend;
+        alpha_pend = 1.f;
+      }
+      if (j >= 2) {  // P[buf] was last read by P.V(j-2): long finished in steady state
+        mbar_wait(&pv_done[buf], ((j - 2) >> 1) & 1);
+        tc_fence_after();
       }
       uint64_t lsum[2] = {0ull, 0ull};
       if (j > 0) {  // speculative P with the running max of the previous tiles
         const uint64_t nm2 = pack2(-m, -m);
         if (full) { exp32<false>(sv, sc2, nm2, lsum, p_tmem, 32); exp32<false>(sv + 32, sc2, nm2, lsum, p_tmem + 16, 32); }
-        else { exp32<true>(sv, sc2, nm2, lsum, p_tmem, vcols); exp32<true>(sv + 32, sc2, nm2, lsum, p_tmem + 16, vcols - 32); }
+        else { exp32<true>(sv, sc2, nm2, lsum, p_tmem, valid); exp32<true>(sv + 32, sc2, nm2, lsum, p_tmem + 16, valid - 32); }
       }
       const bool ovf = !(tmax <= m + 100.f);  // would overflow with the old max; always true for tile 0 (m = -inf)
-      xmax[(par * 128 + r) * 2 + hf] = tmax;
-      const int warp_ovf = __any_sync(0xffffffffu, ovf) ? 1 : 0;
-      if (lane == 0) xflag[(par * 4 + q) * 2 + hf] = warp_ovf;
-      pair_barrier(q);
-      const float tmax_row = fmaxf(tmax, xmax[(par * 128 + r) * 2 + (hf ^ 1)]);
-      const bool redo = (warp_ovf | xflag[(par * 4 + q) * 2 + (hf ^ 1)]) != 0;
-      if (redo) {
+      if (__any_sync(0xffffffffu, ovf)) {
         // exact path: new max >= every logit of this tile; rescale history, recompute P from the registers
-        const float m_new = fmaxf(m, tmax_row);
+        const float m_new = fmaxf(m, tmax);
         if (j > 0) {
           const float alpha = ex2_approx(m - m_new);  // m is finite for j > 0
-          if (__any_sync(0xffffffffu, alpha != 1.f)) rescale_o(alpha);
+          if (__any_sync(0xffffffffu, alpha != 1.f)) {
+            mbar_wait(&pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1);
+            tc_fence_after();
+            rescale_o(alpha);
+          }
           l *= alpha;
         }
         m = m_new;
@@ -347,11 +348,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         lsum[0] = 0ull;
         lsum[1] = 0ull;
         if (full) { exp32<false>(sv, sc2, nm2, lsum, p_tmem, 32); exp32<false>(sv + 32, sc2, nm2, lsum, p_tmem + 16, 32); }
-        else { exp32<true>(sv, sc2, nm2, lsum, p_tmem, vcols); exp32<true>(sv + 32, sc2, nm2, lsum, p_tmem + 16, vcols - 32); }
-      } else if (tmax_row > m + 8.f) {
+        else { exp32<true>(sv, sc2, nm2, lsum, p_tmem, valid); exp32<true>(sv + 32, sc2, nm2, lsum, p_tmem + 16, valid - 32); }
+      } else if (tmax > m + 8.f) {
         // lazy rescale: this tile used the old max; fold the change into O and l before the next tile
-        alpha_pend = ex2_approx(m - tmax_row);
-        m = tmax_row;
+        alpha_pend = ex2_approx(m - tmax);
+        m = tmax;
       }
       {
         float s0, s1, s2, s3;
@@ -362,17 +363,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(p_ready);
+      if (lane == 0) mbar_arrive(&p_ready[buf]);
     }
     // ---- epilogue: O / l -> bf16 -> global (a pending rescale multiplies O and l alike: skipped) ----
-    mbar_wait(pv_done, (n_tiles - 1) & 1);
+    mbar_wait(&pv_done[(n_tiles - 1) & 1], ((n_tiles - 1) >> 1) & 1);
     tc_fence_after();
-    xsum[r * 2 + hf] = l;
-    pair_barrier(q);
-    const float inv_l = 1.0f / (l + xsum[r * 2 + (hf ^ 1)]);
-    bf16* orow = a.out + static_cast<size_t>(q_row0 + qrow) * a.ld_out + col0 + hf * (C::D / 2);
+    const float inv_l = 1.0f / l;
+    bf16* orow = a.out + static_cast<size_t>(q_row0 + qrow) * a.ld_out + col0;
 #pragma unroll 1
-    for (int c = 0; c < C::D / 2; c += 16) {
+    for (int c = 0; c < C::D; c += 16) {
       uint32_t v[16];
       tmem_ld16(o_tmem + c, v);
       tmem_ld_wait();
@@ -395,7 +394,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) {
+  if (warp == 5) {
     tc_fence_after();
     tmem_dealloc(tmem, C::TMEM_COLS);
   }

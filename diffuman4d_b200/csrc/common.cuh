@@ -229,21 +229,69 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
   __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
   return __bfloat1622float2(v);
 }
-__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
-// exact-erf GELU, erf by Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, far below bf16 resolution): 2 MUFU + ~12 FMA-pipe ops
+__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+// ---- packed fp32x2 helpers (sm_100a FFMA2 / FMUL2 / FADD2) ----
+__device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t f2_splat(float v) { return f2_pack(v, v); }
+
+// exact-erf GELU on a pair, erf by Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, far below bf16 resolution):
+// 4 MUFU (2 rcp + 2 ex2) + ~12 packed FMA-pipe ops + 4 ALU ops per PAIR.  Returns a * gelu(g) for both lanes.
+__device__ __forceinline__ uint64_t geglu2(uint64_t a2, uint64_t g2) {
+  float g0, g1;
+  f2_unpack(g2, g0, g1);
+  const uint64_t z = f2_mul(f2_pack(fabsf(g0), fabsf(g1)), f2_splat(0.70710678118654752440f));
+  const uint64_t den = f2_fma(z, f2_splat(0.3275911f), f2_splat(1.0f));
+  float d0, d1;
+  f2_unpack(den, d0, d1);
+  float t0, t1;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(d0));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(d1));
+  const uint64_t t = f2_pack(t0, t1);
+  // -(a1 t + a2 t^2 + ... + a5 t^5), coefficients negated so that erf = 1 + p * exp(-z^2)
+  uint64_t p = f2_fma(f2_splat(-1.061405429f), t, f2_splat(1.453152027f));
+  p = f2_fma(p, t, f2_splat(-1.421413741f));
+  p = f2_fma(p, t, f2_splat(0.284496736f));
+  p = f2_fma(p, t, f2_splat(-0.254829592f));
+  p = f2_mul(p, t);
+  const uint64_t w = f2_mul(f2_mul(z, z), f2_splat(-1.4426950408889634f));
+  float w0, w1, e0, e1;
+  f2_unpack(w, w0, w1);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(w0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(w1));
+  const uint64_t erf_abs = f2_fma(p, f2_pack(e0, e1), f2_splat(1.0f));
+  float r0, r1;
+  f2_unpack(erf_abs, r0, r1);
+  const uint64_t erf_x = f2_pack(copysignf(r0, g0), copysignf(r1, g1));
+  const uint64_t hg = f2_mul(g2, f2_splat(0.5f));
+  const uint64_t gelu = f2_fma(hg, erf_x, hg);
+  return f2_mul(a2, gelu);
+}
 __device__ __forceinline__ float gelu_erf_f(float x) {
-  const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  p *= t;
-  float e;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-z * z * 1.4426950408889634f));
-  const float erf_abs = fmaf(-p, e, 1.0f);          // erf(|x|/sqrt2)
-  const float erf_x = copysignf(erf_abs, x);
-  return 0.5f * x * (1.0f + erf_x);
+  float lo, hi;
+  f2_unpack(geglu2(f2_splat(1.0f), f2_splat(x)), lo, hi);
+  return lo;
 }
 #endif  // __CUDACC__
 

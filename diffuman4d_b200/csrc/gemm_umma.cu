@@ -31,7 +31,8 @@ constexpr int STAGES = 4;
 constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;     // 16 KB
 constexpr int B_BYTES_MAX = 256 * BLOCK_K * 2;     // 32 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES_MAX; // 48 KB
-constexpr int NUM_THREADS = 320;                   // warp0 TMA, warp1 MMA(+TMEM alloc), warps2-9 epilogue
+constexpr int EPI_WARPS_PER_QUARTER = 3;
+constexpr int NUM_THREADS = 64 + 128 * EPI_WARPS_PER_QUARTER;  // warp0 TMA, warp1 MMA(+TMEM alloc), then the epilogue warps
 constexpr int TMEM_COLS = 512;
 constexpr int ACC_STRIDE = 256;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
@@ -65,6 +66,7 @@ __device__ __forceinline__ void add8_bf16(float* f, const uint4& u) {
   p = unpack_bf16x2(u.w); f[6] += p.x; f[7] += p.y;
 }
 
+template <bool kGeglu>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_a2,
                  const __grid_constant__ CUtensorMap tmap_b, const GemmKernelArgs a) {
@@ -93,7 +95,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 8);
+      mbar_init(&tempty[i], 4 * EPI_WARPS_PER_QUARTER);
     }
     fence_mbar_init();
   }
@@ -167,7 +169,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       __syncwarp();
     }
   } else {
-    // ===== epilogue: warps 2..9; TMEM lane quarter = warp%4, the two warps of a quarter take alternate 16-col chunks =====
+    // ===== epilogue warps; TMEM lane quarter = warp%4, the warps of a quarter interleave the 16-col chunks =====
     const int q = warp & 3;
     const int chunk0 = (warp - 2) >> 2;
     const int r = q * 32 + lane;  // row within the 128-row tile
@@ -205,7 +207,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
       // Residual / row-vector loads of chunk c+2 are issued before the TMEM wait of chunk c so that their L2/HBM latency
       // overlaps the TMEM load and the math of the current chunk; bias (L1-resident broadcast) is loaded under the wait.
-      if (!a.geglu) {
+      if (!kGeglu) {
         const int chunks = a.block_n / 16;
         const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
         uint4 r0 = z4, r1 = z4, v0 = z4, v1 = z4, nr0 = z4, nr1 = z4, nv0 = z4, nv1 = z4;
@@ -222,18 +224,18 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             v1 = __ldg(reinterpret_cast<const uint4*>(rv_row + chunk0 * 16 + 8));
           }
         }
-        for (int c = chunk0; c < chunks; c += 2) {
+        for (int c = chunk0; c < chunks; c += EPI_WARPS_PER_QUARTER) {
           uint32_t v[16];
           tmem_ld16(taddr + c * 16, v);
           const int col = n0 + c * 16;
-          if (c + 2 < chunks) {
+          if (c + EPI_WARPS_PER_QUARTER < chunks) {
             if (ld_res) {
-              nr0 = *reinterpret_cast<const uint4*>(res_row + (c + 2) * 16);
-              nr1 = *reinterpret_cast<const uint4*>(res_row + (c + 2) * 16 + 8);
+              nr0 = *reinterpret_cast<const uint4*>(res_row + (c + EPI_WARPS_PER_QUARTER) * 16);
+              nr1 = *reinterpret_cast<const uint4*>(res_row + (c + EPI_WARPS_PER_QUARTER) * 16 + 8);
             }
             if (ld_rv) {
-              nv0 = __ldg(reinterpret_cast<const uint4*>(rv_row + (c + 2) * 16));
-              nv1 = __ldg(reinterpret_cast<const uint4*>(rv_row + (c + 2) * 16 + 8));
+              nv0 = __ldg(reinterpret_cast<const uint4*>(rv_row + (c + EPI_WARPS_PER_QUARTER) * 16));
+              nv1 = __ldg(reinterpret_cast<const uint4*>(rv_row + (c + EPI_WARPS_PER_QUARTER) * 16 + 8));
             }
           }
           float4 b4[4];
@@ -279,7 +281,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         // n_tile*block_n/2 .. +block_n/2
         const int half = a.block_n / 2;
         const int chunks = half / 16;
-        for (int c = chunk0; c < chunks; c += 2) {
+        for (int c = chunk0; c < chunks; c += EPI_WARPS_PER_QUARTER) {
           uint32_t va[16], vg[16];
           tmem_ld16(taddr + c * 16, va);
           tmem_ld16(taddr + half + c * 16, vg);
@@ -295,18 +297,18 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             float o[16];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              float fa0 = __uint_as_float(va[4 * i]), fa1 = __uint_as_float(va[4 * i + 1]);
-              float fa2 = __uint_as_float(va[4 * i + 2]), fa3 = __uint_as_float(va[4 * i + 3]);
-              float fg0 = __uint_as_float(vg[4 * i]), fg1 = __uint_as_float(vg[4 * i + 1]);
-              float fg2 = __uint_as_float(vg[4 * i + 2]), fg3 = __uint_as_float(vg[4 * i + 3]);
+              uint64_t a01 = f2_pack(__uint_as_float(va[4 * i]), __uint_as_float(va[4 * i + 1]));
+              uint64_t a23 = f2_pack(__uint_as_float(va[4 * i + 2]), __uint_as_float(va[4 * i + 3]));
+              uint64_t g01 = f2_pack(__uint_as_float(vg[4 * i]), __uint_as_float(vg[4 * i + 1]));
+              uint64_t g23 = f2_pack(__uint_as_float(vg[4 * i + 2]), __uint_as_float(vg[4 * i + 3]));
               if (a.bias) {
-                fa0 += ba[i].x; fa1 += ba[i].y; fa2 += ba[i].z; fa3 += ba[i].w;
-                fg0 += bg[i].x; fg1 += bg[i].y; fg2 += bg[i].z; fg3 += bg[i].w;
+                a01 = f2_add(a01, f2_pack(ba[i].x, ba[i].y));
+                a23 = f2_add(a23, f2_pack(ba[i].z, ba[i].w));
+                g01 = f2_add(g01, f2_pack(bg[i].x, bg[i].y));
+                g23 = f2_add(g23, f2_pack(bg[i].z, bg[i].w));
               }
-              o[4 * i] = fa0 * gelu_erf_f(fg0);
-              o[4 * i + 1] = fa1 * gelu_erf_f(fg1);
-              o[4 * i + 2] = fa2 * gelu_erf_f(fg2);
-              o[4 * i + 3] = fa3 * gelu_erf_f(fg3);
+              f2_unpack(geglu2(a01, g01), o[4 * i], o[4 * i + 1]);
+              f2_unpack(geglu2(a23, g23), o[4 * i + 2], o[4 * i + 3]);
             }
             const int ocol = n_tile * half + c * 16;
             uint4* op = reinterpret_cast<uint4*>(a.out + static_cast<size_t>(row) * a.ldo + ocol);
@@ -409,9 +411,14 @@ int gemm_prepare(const GemmDesc& d, GemmLaunch* L) {
 }
 
 int gemm_run(const GemmLaunch& L, cudaStream_t stream) {
-  static bool attr_set[64] = {};
-  if (int rc = ensure_dyn_smem(gemm_umma_kernel, SMEM_BYTES, attr_set)) return rc;
-  gemm_umma_kernel<<<L.grid, NUM_THREADS, SMEM_BYTES, stream>>>(L.tmap_a, L.tmap_a2, L.tmap_b, L.args);
+  static bool attr_set[2][64] = {};
+  if (L.args.geglu) {
+    if (int rc = ensure_dyn_smem(gemm_umma_kernel<true>, SMEM_BYTES, attr_set[1])) return rc;
+    gemm_umma_kernel<true><<<L.grid, NUM_THREADS, SMEM_BYTES, stream>>>(L.tmap_a, L.tmap_a2, L.tmap_b, L.args);
+  } else {
+    if (int rc = ensure_dyn_smem(gemm_umma_kernel<false>, SMEM_BYTES, attr_set[0])) return rc;
+    gemm_umma_kernel<false><<<L.grid, NUM_THREADS, SMEM_BYTES, stream>>>(L.tmap_a, L.tmap_a2, L.tmap_b, L.args);
+  }
   D4D_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -49,7 +49,7 @@ __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
 }
 
 // smem: ch_mean[C], ch_m2[C] then scratch [rows_per_iter][C][2]
-__global__ void gn_stats_kernel(const GnArgs a) {
+__global__ void __launch_bounds__(GN_MAX_THREADS, 2) gn_stats_kernel(const GnArgs a) {
   extern __shared__ float sm[];
   const int split = blockIdx.x, img = blockIdx.y;
   const int oct = threadIdx.x % a.n_oct;
@@ -174,7 +174,7 @@ __global__ void gn_stats_kernel(const GnArgs a) {
 }
 
 // smem: g_mean[groups], g_rstd[groups]
-__global__ void gn_apply_kernel(const GnArgs a) {
+__global__ void __launch_bounds__(GN_MAX_THREADS, 2) gn_apply_kernel(const GnArgs a) {
   extern __shared__ float sm[];
   const int split = blockIdx.x, img = blockIdx.y;
   for (int g = threadIdx.x; g < 2 * a.groups; g += blockDim.x)
