@@ -201,8 +201,18 @@ def run_ours(args):
     unet = B200MultiviewUNet(cfg, local).load_state_dict(random_state_dict(cfg, seed=1))
     pipe = B200Diffuman4DPipeline(unet, SchedulerConfig())
     pipe.parepare_schedulers(wl["n_steps"], F)
+    sharded = args.mode == "sharded" and world > 1
+    full_inputs = synth_inputs(F, wl["n_cond"], h, w, seed=0 if sharded else rank)
+    F_total = F
+    sh = None
+    if sharded:   # one window, frames split over the ranks, fused K/V exchange over peer memory
+        from diffuman4d_b200.sharded import FrameShardedPipeline
+        sh = FrameShardedPipeline(pipe, max_frames=F_total, h=h, w=w)
+        lo, hi = sh.frames(F_total)
+        full_inputs = {k: v[lo:hi].contiguous() for k, v in full_inputs.items()}
+        F = hi - lo
     host = {k: (v.to(torch.bfloat16) if v.dtype.is_floating_point else v).pin_memory()
-            for k, v in synth_inputs(F, wl["n_cond"], h, w, seed=rank).items()}
+            for k, v in full_inputs.items()}
     devt = {k: v.to(dev) for k, v in host.items()}
     lat, ts = devt["latents"].clone(), devt["ts"].clone()
 
@@ -211,12 +221,20 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def window_step(latents, pixel, plucker, skel, mask, tsi):
+        if sh is not None:
+            sh.denoise_window(latents=latents, pixel_values_latents=pixel, plucker_embeds_latents=plucker,
+                              skeletons_latents=skel, cond_masks_latents=mask, timestep_indices=tsi, domain=wl["domain"],
+                              guidance_scale=wl["guidance"], F_total=F_total)
+        else:
+            pipe.denoise_window(latents=latents, pixel_values_latents=pixel, plucker_embeds_latents=plucker,
+                                skeletons_latents=skel, cond_masks_latents=mask, timestep_indices=tsi,
+                                domain=wl["domain"], guidance_scale=wl["guidance"])
+
     def step_resident():
         lat.copy_(devt["latents"])
         ts.copy_(devt["ts"])
-        pipe.denoise_window(latents=lat, pixel_values_latents=devt["pixel"], plucker_embeds_latents=devt["plucker"],
-                            skeletons_latents=devt["skel"], cond_masks_latents=devt["mask"], timestep_indices=ts,
-                            domain=wl["domain"], guidance_scale=wl["guidance"])
+        window_step(lat, devt["pixel"], devt["plucker"], devt["skel"], devt["mask"], ts)
 
     out_host = torch.empty_like(host["latents"]).pin_memory()
     ts_host = torch.empty_like(host["ts"]).pin_memory()
@@ -225,10 +243,7 @@ def run_ours(args):
     def step_e2e():
         for k in ("latents", "pixel", "plucker", "skel", "mask", "ts"):
             stage[k].copy_(host[k], non_blocking=True)
-        pipe.denoise_window(latents=stage["latents"], pixel_values_latents=stage["pixel"],
-                            plucker_embeds_latents=stage["plucker"], skeletons_latents=stage["skel"],
-                            cond_masks_latents=stage["mask"], timestep_indices=stage["ts"], domain=wl["domain"],
-                            guidance_scale=wl["guidance"])
+        window_step(stage["latents"], stage["pixel"], stage["plucker"], stage["skel"], stage["mask"], stage["ts"])
         out_host.copy_(stage["latents"], non_blocking=True)
         ts_host.copy_(stage["ts"], non_blocking=True)
         torch.cuda.current_stream().synchronize()
@@ -257,10 +272,12 @@ def run_ours(args):
     assert torch.isfinite(out_host.float()).all(), "non-finite latents out of the window step"
 
     # ---- live per-kernel-kind device times of the UNet forward (CUDA events around every launch) ----
+    F = F_total        # the profile below always runs the full single-GPU window
     B = 2 * F
     x = torch.randn(B, cfg.in_channels, h, w, device=dev).to(torch.bfloat16)
     tt = torch.randint(0, 1000, (B,), device=dev)
-    sk = torch.cat([-torch.ones_like(devt["skel"]), devt["skel"]])
+    skp = torch.rand(F, 3, 8 * h, 8 * w, device=dev).to(torch.bfloat16) * 2 - 1
+    sk = torch.cat([-torch.ones_like(skp), skp])
     y = torch.empty(B, 4, h, w, device=dev, dtype=torch.bfloat16)
     doms = (C.c_int32 * 2)(0, 0)
     ms_k, n_k, fl_k = (C.c_float * 6)(), (C.c_int32 * 6)(), (C.c_double * 6)()
@@ -293,22 +310,25 @@ def run_ours(args):
                 "by_kind_tflops": {names[k]: round(alg[k] / (kind_ms[k] * 1e-3) / 1e12, 1) for k in (0, 1, 2)},
                 "unet_forward_ms_sum": round(sum(kind_ms), 3)}
 
-    value = world * args.steps / (ms_res * 1e-3)
-    e2e_val = world * args.steps / (ms_e2e * 1e-3)
+    jobs = 1 if sharded else world   # sharded: all ranks cooperate on ONE window per step (strong scaling)
+    value = jobs * args.steps / (ms_res * 1e-3)
+    e2e_val = jobs * args.steps / (ms_e2e * 1e-3)
     h2d = sum(host[k].numel() * host[k].element_size() for k in ("latents", "pixel", "plucker", "skel", "mask", "ts"))
     d2h = out_host.numel() * 2 + ts_host.numel() * 8
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "strong" if sharded else "weak",
+        "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
         "config": {"workload": wl["name"], "unet": "SD-2.1 layout 320/640/1280/1280, heads 5/10/20/20, in_channels 11 "
                    "(pose encoder + frame-index embedding), no attn2", "images_per_step": B,
-                   "parallelism": f"replicas x{world} (independent windows, no collective)" if world > 1 else "single GPU",
+                   "parallelism": (f"frame-sharded window x{world} (fused K/V exchange over NVLink peer memory)" if sharded else
+                                   f"replicas x{world} (independent windows, no collective)" if world > 1 else "single GPU"),
                    "l2": f"no explicit flush: one step streams ~{unet.workspace_bytes(2, B, F, h, w) / 2**30:.1f} GiB of "
                          "activations + 1.6 GB of weights through a 126 MB L2"},
         "tflops_per_step": fl["total"] / 1e12,
-        "unet_tflops_achieved": fl["total"] / (ms_res / args.steps * 1e-3) / 1e12,
-        "unet_roofline_frac": fl["total"] / (ms_res / args.steps * 1e-3) / 1e12 / peak_tf,
+        "unet_tflops_achieved": jobs * fl["total"] / (ms_res / args.steps * 1e-3) / 1e12,
+        "unet_roofline_frac": jobs * fl["total"] / (ms_res / args.steps * 1e-3) / 1e12 / peak_tf / world,
         "roofline": roofline, "clocks": clocks,
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / args.steps},
@@ -330,6 +350,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="replicas", choices=["replicas", "sharded"],
+                    help="N>1: independent windows per GPU (weak) or one frame-sharded window over all GPUs (strong)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -13,8 +13,8 @@ EXPORTS = [
     "d4d_last_error", "d4d_version", "d4d_create", "d4d_destroy", "d4d_load_weight", "d4d_finalize_weights",
     "d4d_num_weights", "d4d_weight_key", "d4d_unet_forward", "d4d_profile_forward", "d4d_workspace_bytes", "d4d_forward_launches",
     "d4d_denoise_window", "d4d_assemble_input", "d4d_cfg_ddim_step", "d4d_op_gemm", "d4d_op_conv3x3",
-    "d4d_op_attention", "d4d_op_groupnorm", "d4d_op_layernorm", "d4d_op_probe_umma", "d4d_kv_exchange_bytes",
-    "d4d_set_peers",
+    "d4d_op_attention", "d4d_op_groupnorm", "d4d_op_layernorm", "d4d_op_probe_umma", "d4d_exchange_alloc",
+    "d4d_exchange_open", "d4d_unet_forward_sharded", "d4d_denoise_window_sharded",
 ]
 
 
@@ -80,12 +80,16 @@ def lib() -> C.CDLL:
     l.d4d_op_groupnorm.argtypes = [vp, i32, vp, i32, i32, i32, i32, f32, f32p, f32p, i32, vp, vp]
     l.d4d_op_layernorm.argtypes = [vp, i32, i32, f32, f32p, f32p, vp, vp]
     l.d4d_op_probe_umma.argtypes = [vp, vp, vp, i32, i32, i32, i32, u32, u32, u32, vp]
-    l.d4d_kv_exchange_bytes.argtypes = [vp, i32, i32, i32, i32, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
-    l.d4d_set_peers.argtypes = [vp, i32, i32, C.POINTER(vp), C.POINTER(vp)]
+    l.d4d_exchange_alloc.argtypes = [vp, C.c_size_t, vp]
+    l.d4d_exchange_open.argtypes = [vp, i32, i32, vp]
+    l.d4d_unet_forward_sharded.argtypes = [vp, vp, vp, vp, C.POINTER(C.c_int32), i32, i32, i32, i32, i32, i32, vp, vp]
+    l.d4d_denoise_window_sharded.argtypes = [vp, vp, vp, vp, vp, vp, vp, C.POINTER(D4DSched), f32, i32, i32, i32, i32,
+                                             i32, i32, vp]
     for name in EXPORTS:
         fn = getattr(l, name)
         if fn.restype is C.c_int or name.startswith("d4d_op_") or name in (
-                "d4d_create", "d4d_load_weight", "d4d_finalize_weights", "d4d_unet_forward", "d4d_denoise_window"):
+                "d4d_create", "d4d_load_weight", "d4d_finalize_weights", "d4d_unet_forward", "d4d_denoise_window",
+                "d4d_exchange_alloc", "d4d_exchange_open", "d4d_unet_forward_sharded", "d4d_denoise_window_sharded"):
             fn.restype = C.c_int
     _lib = l
     return l

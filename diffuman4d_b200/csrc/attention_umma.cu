@@ -290,20 +290,21 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       }
     };
 
+    // S(j) lives in `sv`; the TMEM loads of S(j+1) are issued at the end of iteration j (after the last use of sv) so
+    // that their latency overlaps the P-store drain and the barrier traffic of tile j (software pipelining, no extra regs)
+    uint32_t sv[64];
+    mbar_wait(&s_full[0], 0);
+    tc_fence_after();
+    tmem_ld32(tmem + C::COL_S + lane_sel, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
+    tmem_ld32(tmem + C::COL_S + lane_sel + 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[32]));
+
     for (int j = 0; j < n_tiles; ++j) {
       const int valid = min(BLOCK_KV, a.seq_kv - j * BLOCK_KV);
       const bool full = valid == BLOCK_KV;
       const int buf = j & 1;
       const uint32_t par = (j >> 1) & 1;
-      const uint32_t s_tmem = tmem + C::COL_S + buf * 64 + lane_sel;
       const uint32_t p_tmem = tmem + C::COL_P + buf * 32 + lane_sel;
-      mbar_wait(&s_full[buf], par);
-      tc_fence_after();
-      // S(j) -> registers (one exposed TMEM latency per tile), then release the buffer for Q.K(j+2)
-      uint32_t sv[64];
-      tmem_ld32(s_tmem, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
-      tmem_ld32(s_tmem + 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[32]));
-      tmem_ld_wait();
+      tmem_ld_wait();  // S(j) is in registers: release the buffer for Q.K(j+2)
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_free[buf]);
@@ -360,11 +361,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         unpack2(lsum[1], s2, s3);
         l += (s0 + s1) + (s2 + s3);
       }
+      if (j + 1 < n_tiles) {  // prefetch S(j+1) (ready long ago: Q.K runs two tiles ahead)
+        mbar_wait(&s_full[buf ^ 1], ((j + 1) >> 1) & 1);
+        tc_fence_after();
+        const uint32_t s_next = tmem + C::COL_S + (buf ^ 1) * 64 + lane_sel;
+        tmem_ld32(s_next, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
+        tmem_ld32(s_next + 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[32]));
+      }
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_ready[buf]);
     }
+    tmem_ld_wait();
     // ---- epilogue: O / l -> bf16 -> global (a pending rescale multiplies O and l alike: skipped) ----
     mbar_wait(&pv_done[(n_tiles - 1) & 1], ((n_tiles - 1) >> 1) & 1);
     tc_fence_after();

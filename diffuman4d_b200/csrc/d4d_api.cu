@@ -305,22 +305,46 @@ int d4d_op_probe_umma(const void* A, const void* B, float* D, int N, int K, int 
   D4D_API_END
 }
 
-int d4d_kv_exchange_bytes(d4d_handle* h, int B, int F, int height, int width, size_t* kv_bytes, size_t* flag_bytes) {
+int d4d_unet_forward_sharded(d4d_handle* h, const void* sample, const int64_t* timestep, const void* skeletons,
+                             const int32_t* domain_ids, int n_domains, int B_local, int F_local, int F_total, int height,
+                             int width, void* out, void* stream) {
   D4D_API_BEGIN
-  D4D_REQUIRE(h != nullptr && kv_bytes != nullptr && flag_bytes != nullptr, "null argument");
-  (void)B; (void)F; (void)height; (void)width;
-  d4d::set_error("multi-GPU K/V exchange is not built in this version");
-  return 1;
+  D4D_REQUIRE(h != nullptr, "null handle");
+  DeviceGuard g(h->model->device());
+  return h->model->forward(static_cast<const bf16*>(sample), reinterpret_cast<const long long*>(timestep),
+                           static_cast<const bf16*>(skeletons), domain_ids, n_domains, B_local, F_local, height, width,
+                           static_cast<bf16*>(out), static_cast<cudaStream_t>(stream), F_total);
   D4D_API_END
 }
 
-int d4d_set_peers(d4d_handle* h, int rank, int world, void* const* peer_kv, void* const* peer_flags) {
+int d4d_denoise_window_sharded(d4d_handle* h, void* latents, const void* pixel_latents, const void* plucker,
+                               const void* skeletons, const void* cond_mask, int64_t* timestep_indices,
+                               const d4d_sched* sched, float guidance_scale, int domain, int F_local, int F_total,
+                               int height, int width, int num_steps, void* stream) {
+  D4D_API_BEGIN
+  D4D_REQUIRE(h != nullptr && sched != nullptr, "null argument");
+  DeviceGuard g(h->model->device());
+  return h->model->denoise_window(static_cast<bf16*>(latents), static_cast<const bf16*>(pixel_latents),
+                                  static_cast<const bf16*>(plucker), static_cast<const bf16*>(skeletons),
+                                  static_cast<const bf16*>(cond_mask), reinterpret_cast<long long*>(timestep_indices),
+                                  *sched, guidance_scale, domain, F_local, height, width, num_steps,
+                                  static_cast<cudaStream_t>(stream), F_total);
+  D4D_API_END
+}
+
+int d4d_exchange_alloc(d4d_handle* h, size_t kv_bytes, unsigned char* handles_out) {
   D4D_API_BEGIN
   D4D_REQUIRE(h != nullptr, "null handle");
-  (void)rank; (void)peer_kv; (void)peer_flags;
-  if (world == 1) return 0;
-  d4d::set_error("multi-GPU K/V exchange is not built in this version");
-  return 1;
+  DeviceGuard g(h->model->device());
+  return h->model->exchange_alloc(kv_bytes, handles_out);
+  D4D_API_END
+}
+
+int d4d_exchange_open(d4d_handle* h, int rank, int world, const unsigned char* all_handles) {
+  D4D_API_BEGIN
+  D4D_REQUIRE(h != nullptr, "null handle");
+  DeviceGuard g(h->model->device());
+  return h->model->exchange_open(rank, world, all_handles);
   D4D_API_END
 }
 

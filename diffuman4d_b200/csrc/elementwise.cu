@@ -297,6 +297,32 @@ __global__ void cfg_ddim_kernel(const DdimArgs a, long long* ts_out) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// frame-sharded window: K/V arrival flags in peer memory
+// ---------------------------------------------------------------------------------------------
+__global__ void kv_signal_kernel(const KvFlagArgs a) {
+  const int r = threadIdx.x;
+  if (r >= a.world) return;
+  __threadfence_system();  // order the K/V stores of the preceding kernels (this stream) before the flag
+  unsigned int* f = a.flags[r] + a.slot * 8 + a.rank;
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(a.epoch) : "memory");
+}
+__global__ void kv_wait_kernel(const KvFlagArgs a) {
+  const int r = threadIdx.x;
+  if (r >= a.world) return;
+  const unsigned int* f = a.flags[a.rank] + a.slot * 8 + r;
+  unsigned int v = 0;
+  unsigned long long spins = 0;
+  do {
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+    if (++spins > (1ull << 31)) {  // ~ seconds: a lost peer must trap, not hang the box
+      printf("d4d: K/V flag timeout rank=%d waiting for rank=%d epoch=%u have=%u\n", a.rank, r, a.epoch, v);
+      __trap();
+    }
+  } while (static_cast<int>(v - a.epoch) < 0);
+  __threadfence_system();
+}
+
 inline int blocks_for(long long total, int threads) { return static_cast<int>((total + threads - 1) / threads); }
 
 }  // namespace
@@ -381,6 +407,17 @@ int direct_conv_run(const bf16* x, int in_nchw, int n, int Cin, int H, int W, co
       return 1;
   }
 #undef D4D_DC
+  D4D_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int kv_signal_run(const KvFlagArgs& a, cudaStream_t stream) {
+  kv_signal_kernel<<<1, 32, 0, stream>>>(a);
+  D4D_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+int kv_wait_run(const KvFlagArgs& a, cudaStream_t stream) {
+  kv_wait_kernel<<<1, 32, 0, stream>>>(a);
   D4D_CUDA_OK(cudaGetLastError());
   return 0;
 }

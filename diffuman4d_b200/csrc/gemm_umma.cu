@@ -265,14 +265,28 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               for (int i = 0; i < 16; ++i) f[i] *= a.out_scale;
             }
             if (a.residual) { add8_bf16(f, r0); add8_bf16(f + 8, r1); }
-            uint4* op = reinterpret_cast<uint4*>(a.out + static_cast<size_t>(row) * a.ldo + col);
             uint4 o0, o1;
             o0.x = pack_bf16x2(f[0], f[1]);   o0.y = pack_bf16x2(f[2], f[3]);
             o0.z = pack_bf16x2(f[4], f[5]);   o0.w = pack_bf16x2(f[6], f[7]);
             o1.x = pack_bf16x2(f[8], f[9]);   o1.y = pack_bf16x2(f[10], f[11]);
             o1.z = pack_bf16x2(f[12], f[13]); o1.w = pack_bf16x2(f[14], f[15]);
-            op[0] = o0;
-            op[1] = o1;
+            if (a.kv_world > 0 && col >= a.kv_col0) {
+              // fused all-gather: the K|V columns of the QKV projection go straight into every rank's gathered
+              // K/V buffer (peer memory over NVLink; own rank included) at this rank's global token rows
+              const long long half = row / a.kv_rows_local;
+              const long long grow = half * a.kv_rows_global + a.kv_row_offset + (row - half * a.kv_rows_local);
+              const size_t off = static_cast<size_t>(grow) * a.kv_ld + (col - a.kv_col0);
+#pragma unroll 1
+              for (int rk = 0; rk < a.kv_world; ++rk) {
+                uint4* dp = reinterpret_cast<uint4*>(a.kv_dst[rk] + off);
+                dp[0] = o0;
+                dp[1] = o1;
+              }
+            } else {
+              uint4* op = reinterpret_cast<uint4*>(a.out + static_cast<size_t>(row) * a.ldo + col);
+              op[0] = o0;
+              op[1] = o1;
+            }
           }
           r0 = nr0; r1 = nr1; v0 = nv0; v1 = nv1;
         }
@@ -359,6 +373,14 @@ int gemm_prepare(const GemmDesc& d, GemmLaunch* L) {
   a.geglu = d.geglu;
   a.act = d.act;
   a.out_scale = d.out_scale;
+  a.kv_world = d.kv_world;
+  a.kv_col0 = d.kv_col0;
+  a.kv_ld = d.kv_ld;
+  a.kv_rows_local = d.kv_rows_local > 0 ? d.kv_rows_local : 1;
+  a.kv_rows_global = d.kv_rows_global;
+  a.kv_row_offset = d.kv_row_offset;
+  for (int i = 0; i < 8; ++i) a.kv_dst[i] = d.kv_dst[i];
+  D4D_REQUIRE(d.kv_world >= 0 && d.kv_world <= 8 && (d.kv_world == 0 || (d.kv_col0 % 16 == 0 && d.kv_ld % 8 == 0 && !d.geglu)), "K/V scatter arguments");
   D4D_REQUIRE(d.ldo % 8 == 0 && (d.residual == nullptr || d.ld_res % 8 == 0) &&
               (d.rowvec == nullptr || d.ld_rowvec % 8 == 0), "leading dimensions must be multiples of 8");
 

@@ -25,6 +25,10 @@ struct GemmKernelArgs {
   int geglu;
   int act;          // 0 none, 1 SiLU applied to (acc + bias + rowvec) before scale/residual
   float out_scale;  // multiplies (acc + bias + rowvec) after the activation
+  // fused K/V all-gather (frame-sharded window): columns >= kv_col0 are stored into every rank's gathered buffer
+  int kv_world, kv_col0, kv_ld;
+  long long kv_rows_local, kv_rows_global, kv_row_offset;
+  bf16* kv_dst[8];
 };
 
 struct GemmDesc {
@@ -46,6 +50,11 @@ struct GemmDesc {
   int act = 0;
   float out_scale = 1.0f;
   int block_n = 0;  // 0 = auto
+  // fused K/V all-gather: rows of CFG half h (local row / kv_rows_local) land at global row
+  // h*kv_rows_global + kv_row_offset + (local row % kv_rows_local) of every kv_dst[r] (leading dim kv_ld)
+  int kv_world = 0, kv_col0 = 0, kv_ld = 0;
+  long long kv_rows_local = 0, kv_rows_global = 0, kv_row_offset = 0;
+  bf16* kv_dst[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   // conv3x3: A is NHWC [n_img, H, W, Cin]
   int conv = 0, n_img = 0, H = 0, W = 0, Cin = 0;
 };
@@ -165,6 +174,17 @@ struct DdimArgs {
 };
 // ts_out[F]: updated timestep indices (targets +1, cond 0); may not alias a.timestep_indices
 int cfg_ddim_step_run(const DdimArgs& a, long long* ts_out, cudaStream_t stream);
+
+// cross-rank K/V arrival flags (frame-sharded window): signal = system-scope release of `epoch` into slot `my_rank` of
+// every rank's flag array; wait = acquire-spin until all `world` slots of the local array reach `epoch`
+struct KvFlagArgs {
+  unsigned int* flags[8];  // flags[r] = rank r's array (peer mapped); flags[my_rank] is local
+  int rank, world;
+  unsigned int epoch;
+  int slot;                // parity slot: arrays are [2][8]
+};
+int kv_signal_run(const KvFlagArgs& a, cudaStream_t stream);
+int kv_wait_run(const KvFlagArgs& a, cudaStream_t stream);
 
 // UMMA operand-encoding probe (probe.cu)
 int probe_umma_run(const bf16* A, const bf16* B, float* D, int N, int K, int a_src, int b_major, uint32_t b_lbo,

@@ -582,16 +582,79 @@ class PlanBuilder {
     return {out, r.cout, xa.H, xa.W};
   }
 
-  void self_attention(const AttnW& a, const XfW& x, const bf16* normed, const bf16* resid, bf16* out, int M, int batch, int seq) {
+  // Frame-sharded 3-D attention: the QKV GEMM epilogue stores its K|V columns straight into every rank's gathered
+  // K/V buffer (peer memory), a flag round makes them visible, attention reads all F_total frames locally.
+  void sharded_qkv_attention(const AttnW& a, const XfW& x, const bf16* normed, bf16* qkv, bf16* o, int M, int batch, int seq) {
     const int Cp = x.heads * x.dpad;
-    bf16* qkv = alloc(static_cast<size_t>(M) * 3 * Cp);
-    {
+    const Exchange& X = m_.xch_;
+    const int idx = p_.n3d++;
+    p_.launches += 4;
+    const long long rows_local = seq;                                   // F_loc * hw tokens per CFG half
+    const long long rows_global = static_cast<long long>(seq) / p_.F * p_.F_total;
+    if (static_cast<size_t>(batch) * rows_global * 2 * Cp * sizeof(bf16) > X.kv_bytes) {
+      set_error("K/V exchange buffer too small for this window (d4d_exchange_alloc)");
+      if (!rc_) rc_ = 1;
+      return;
+    }
+    if (dry_) return;
+    GemmLaunch G[2];
+    AttnLaunch A[2];
+    for (int par = 0; par < 2; ++par) {
       GemmDesc d;
       d.A = normed; d.lda = x.C; d.K1 = x.C; d.Wt = a.qkv.w; d.M = M; d.N = 3 * Cp; d.out = qkv; d.ldo = 3 * Cp;
-      gemm(d);
+      d.kv_world = X.world; d.kv_col0 = Cp; d.kv_ld = 2 * Cp;
+      d.kv_rows_local = rows_local; d.kv_rows_global = rows_global; d.kv_row_offset = static_cast<long long>(X.rank) * rows_local;
+      for (int r = 0; r < X.world; ++r) d.kv_dst[r] = static_cast<bf16*>(X.peer_kv[par][r]);
+      if (int rc = gemm_prepare(d, &G[par])) { if (!rc_) rc_ = rc; return; }
+      AttnDesc t;
+      t.q = qkv; t.ld_qkv = 3 * Cp;
+      t.k = static_cast<const bf16*>(X.kv[par]); t.v = t.k + Cp; t.ld_kv = 2 * Cp;
+      t.out = o; t.ld_out = Cp; t.batch = batch; t.seq = seq; t.seq_kv = static_cast<int>(rows_global);
+      t.heads = x.heads; t.head_dim = x.dpad; t.scale = 1.0f / sqrtf(static_cast<float>(x.d));
+      if (int rc = attn_prepare(t, &A[par])) { if (!rc_) rc_ = rc; return; }
     }
-    bf16* o = alloc(static_cast<size_t>(M) * Cp);
-    {
+    KvFlagArgs fa;
+    for (int r = 0; r < 8; ++r) fa.flags[r] = r < X.world ? X.peer_flags[r] : nullptr;
+    fa.rank = X.rank; fa.world = X.world; fa.epoch = 0; fa.slot = 0;
+    Plan* pl = &p_;
+    const GemmLaunch G0 = G[0], G1 = G[1];
+    const AttnLaunch A0 = A[0], A1 = A[1];
+    const double fl_g = gemm_flops(G0), fl_a = attn_flops(A0.d);
+    p_.ops.push_back([=](cudaStream_t s) {
+      const unsigned int counter = pl->epoch0 + idx;
+      const int par = counter & 1;
+      if (int rc = gemm_run(par ? G1 : G0, s)) return rc;
+      KvFlagArgs f = fa;
+      f.epoch = counter + 1;
+      f.slot = par;
+      if (int rc = kv_signal_run(f, s)) return rc;
+      return kv_wait_run(f, s);
+    });
+    p_.op_kind.push_back(0);
+    p_.op_flops.push_back(fl_g);
+    p_.ops.push_back([=](cudaStream_t s) {
+      const unsigned int counter = pl->epoch0 + idx;
+      return attn_run((counter & 1) ? A1 : A0, s);
+    });
+    p_.op_kind.push_back(2);
+    p_.op_flops.push_back(fl_a);
+  }
+
+  void self_attention(const AttnW& a, const XfW& x, const bf16* normed, const bf16* resid, bf16* out, int M, int batch, int seq,
+                      bool is3d = false) {
+    const int Cp = x.heads * x.dpad;
+    bf16* qkv = alloc(static_cast<size_t>(M) * 3 * Cp);
+    bf16* o = nullptr;
+    if (is3d && p_.world > 1) {
+      o = alloc(static_cast<size_t>(M) * Cp);
+      sharded_qkv_attention(a, x, normed, qkv, o, M, batch, seq);
+    } else {
+      {
+        GemmDesc d;
+        d.A = normed; d.lda = x.C; d.K1 = x.C; d.Wt = a.qkv.w; d.M = M; d.N = 3 * Cp; d.out = qkv; d.ldo = 3 * Cp;
+        gemm(d);
+      }
+      o = alloc(static_cast<size_t>(M) * Cp);
       AttnDesc d;
       d.q = qkv; d.k = qkv + Cp; d.v = qkv + 2 * Cp; d.ld_qkv = 3 * Cp;
       d.out = o; d.ld_out = Cp; d.batch = batch; d.seq = seq; d.heads = x.heads; d.head_dim = x.dpad;
@@ -622,7 +685,7 @@ class PlanBuilder {
     // attn1 (3-D when num_frames > 1: batch = B / num_frames sequences of num_frames*hw tokens)
     layernorm(t, M, C, x.ln1, n);
     bf16* t1 = alloc(static_cast<size_t>(M) * C);
-    self_attention(x.a1, x, n, t, t1, M, B / num_frames, num_frames * hw);
+    self_attention(x.a1, x, n, t, t1, M, B / num_frames, num_frames * hw, num_frames > 1);
     release(t);
     if (x.has2) {  // attn2 with encoder_hidden_states=None: per-image self-attention
       layernorm(t1, M, C, x.ln2, n);
@@ -705,7 +768,7 @@ class PlanBuilder {
       if (!dry_) {
         std::vector<float> hp(B);
         for (int dmn = 0; dmn < p_.n_domains; ++dmn)
-          for (int f = 0; f < F; ++f) hp[dmn * F + f] = p_.domains[dmn] == 0 ? 0.f : static_cast<float>(f % std::max(1, F / 2));
+          for (int f = 0; f < F; ++f) hp[dmn * F + f] = p_.domains[dmn] == 0 ? 0.f : static_cast<float>((p_.rank * F + f) % std::max(1, (p_.world > 1 ? p_.F_total : F) / 2));
         if (cudaMemcpy(pos, hp.data(), sizeof(float) * B, cudaMemcpyHostToDevice) != cudaSuccess) rc_ = 2;
       }
       op([=](cudaStream_t s) { return sinusoid_run(pos, B, C0, 1, 0.f, tsin, s); });
@@ -898,7 +961,7 @@ Plan* Model::find_plan(int n_domains, int B, int F, int h, int w) {
   return nullptr;
 }
 
-int Model::get_plan(const int* domain_ids, int n_domains, int B, int F, int h, int w, Plan** out) {
+int Model::get_plan(const int* domain_ids, int n_domains, int B, int F, int h, int w, Plan** out, int F_total) {
   if (!finalized_) {
     set_error("weights not finalized (call d4d_finalize_weights)");
     return 3;
@@ -911,7 +974,12 @@ int Model::get_plan(const int* domain_ids, int n_domains, int B, int F, int h, i
   }
   D4D_REQUIRE(h % 8 == 0 && w % 8 == 0 && h > 0 && w > 0, "latent height/width must be divisible by 8");
   for (int i = 0; i < n_domains; ++i) D4D_REQUIRE(domain_ids[i] == 0 || domain_ids[i] == 1, "Invalid domain for temporal embedding");
-  const std::string key = plan_key(domain_ids, n_domains, B, F, h, w);
+  const bool sharded = F_total > F;
+  if (sharded) {
+    D4D_REQUIRE(xch_.ready && xch_.world > 1, "frame-sharded forward needs d4d_exchange_open first");
+    D4D_REQUIRE(F * xch_.world == F_total, "F_total must equal world * local frames");
+  }
+  const std::string key = plan_key(domain_ids, n_domains, B, F, h, w) + (sharded ? "_sh" + std::to_string(F_total) : std::string());
   auto it = plans_.find(key);
   if (it != plans_.end()) {
     *out = it->second.get();
@@ -921,11 +989,13 @@ int Model::get_plan(const int* domain_ids, int n_domains, int B, int F, int h, i
   std::unique_ptr<Plan> p(new Plan());
   p->n_domains = n_domains; p->B = B; p->F = F; p->h = h; p->w = w;
   p->domains.assign(domain_ids, domain_ids + n_domains);
+  if (sharded) { p->F_total = F_total; p->rank = xch_.rank; p->world = xch_.world; }
   size_t peak = 0;
   {
     Plan scratch;
     scratch.n_domains = n_domains; scratch.B = B; scratch.F = F; scratch.h = h; scratch.w = w;
     scratch.domains = p->domains;
+    scratch.F_total = p->F_total; scratch.rank = p->rank; scratch.world = p->world;
     PlanBuilder dry(*this, scratch, true, nullptr);
     if (int rc = dry.build()) return rc;
     peak = dry.peak();
@@ -940,19 +1010,74 @@ int Model::get_plan(const int* domain_ids, int n_domains, int B, int F, int h, i
 }
 
 int Model::forward(const bf16* sample, const long long* timestep, const bf16* skeletons, const int* domain_ids,
-                   int n_domains, int B, int F, int h, int w, bf16* out, cudaStream_t stream) {
+                   int n_domains, int B, int F, int h, int w, bf16* out, cudaStream_t stream, int F_total) {
   D4D_REQUIRE(sample && timestep && out && domain_ids, "null argument");
   D4D_REQUIRE(!cfg_.enable_pose_encoder || skeletons != nullptr, "skeletons are required when enable_pose_encoder");
   D4D_REQUIRE(!cfg_.center_input_sample, "center_input_sample is not supported");
   Plan* p = nullptr;
-  if (int rc = get_plan(domain_ids, n_domains, B, F, h, w, &p)) return rc;
+  if (int rc = get_plan(domain_ids, n_domains, B, F, h, w, &p, F_total)) return rc;
   D4D_CUDA_OK(cudaSetDevice(device_));
   p->sample = sample;
   p->timestep = timestep;
   p->skeletons = skeletons;
   p->out = out;
+  p->epoch0 = xch_.epoch_base;  // global, monotonic exchange counter: every rank runs the same forwards in the same order
   for (auto& f : p->ops)
     if (int rc = f(stream)) return rc;
+  p->run_index++;
+  xch_.epoch_base += static_cast<unsigned int>(p->n3d);
+  return 0;
+}
+
+int Model::exchange_alloc(size_t kv_bytes, unsigned char* handles_out) {
+  D4D_REQUIRE(handles_out != nullptr && kv_bytes > 0, "exchange_alloc arguments");
+  D4D_REQUIRE(xch_.kv[0] == nullptr, "exchange buffers already allocated");
+  D4D_CUDA_OK(cudaSetDevice(device_));
+  for (int i = 0; i < 2; ++i) {
+    D4D_CUDA_OK(cudaMalloc(&xch_.kv[i], kv_bytes));
+    dev_allocs_.push_back(xch_.kv[i]);
+  }
+  void* fl = nullptr;
+  D4D_CUDA_OK(cudaMalloc(&fl, 64 * sizeof(unsigned int)));
+  D4D_CUDA_OK(cudaMemset(fl, 0, 64 * sizeof(unsigned int)));
+  dev_allocs_.push_back(fl);
+  xch_.flags = static_cast<unsigned int*>(fl);
+  xch_.kv_bytes = kv_bytes;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  cudaIpcMemHandle_t hnd;
+  void* ptrs[3] = {xch_.kv[0], xch_.kv[1], fl};
+  for (int i = 0; i < 3; ++i) {
+    D4D_CUDA_OK(cudaIpcGetMemHandle(&hnd, ptrs[i]));
+    memcpy(handles_out + 64 * i, &hnd, 64);
+  }
+  return 0;
+}
+
+int Model::exchange_open(int rank, int world, const unsigned char* all_handles) {
+  D4D_REQUIRE(all_handles != nullptr && world >= 1 && world <= 8 && rank >= 0 && rank < world, "exchange_open arguments");
+  D4D_REQUIRE(xch_.kv[0] != nullptr, "call d4d_exchange_alloc first");
+  D4D_REQUIRE(!xch_.ready, "exchange already opened");
+  D4D_CUDA_OK(cudaSetDevice(device_));
+  for (int r = 0; r < world; ++r) {
+    if (r == rank) {
+      xch_.peer_kv[0][r] = xch_.kv[0];
+      xch_.peer_kv[1][r] = xch_.kv[1];
+      xch_.peer_flags[r] = xch_.flags;
+      continue;
+    }
+    void* ptrs[3];
+    for (int i = 0; i < 3; ++i) {
+      cudaIpcMemHandle_t hnd;
+      memcpy(&hnd, all_handles + (static_cast<size_t>(r) * 3 + i) * 64, 64);
+      D4D_CUDA_OK(cudaIpcOpenMemHandle(&ptrs[i], hnd, cudaIpcMemLazyEnablePeerAccess));
+    }
+    xch_.peer_kv[0][r] = ptrs[0];
+    xch_.peer_kv[1][r] = ptrs[1];
+    xch_.peer_flags[r] = static_cast<unsigned int*>(ptrs[2]);
+  }
+  xch_.rank = rank;
+  xch_.world = world;
+  xch_.ready = true;
   return 0;
 }
 
@@ -990,7 +1115,7 @@ int Model::profile(const bf16* sample, const long long* timestep, const bf16* sk
 
 int Model::denoise_window(bf16* latents, const bf16* pixel, const bf16* plucker, const bf16* skeletons, const bf16* mask,
                           long long* ts_idx, const d4d_sched& sched, float guidance, int domain, int F, int h, int w,
-                          int num_steps, cudaStream_t stream) {
+                          int num_steps, cudaStream_t stream, int F_total) {
   D4D_REQUIRE(latents && pixel && plucker && mask && ts_idx, "null argument");
   D4D_REQUIRE(sched.timesteps_table && sched.alphas_cumprod && sched.n_steps > 0, "scheduler tables");
   D4D_REQUIRE(domain == 0 || domain == 1, "Invalid domain");
@@ -1033,7 +1158,7 @@ int Model::denoise_window(bf16* latents, const bf16* pixel, const bf16* plucker,
         skel_in = skeletons;
       }
     }
-    if (int rc = forward(wb.sample, wb.timestep, skel_in, doms, cfg_on ? 2 : 1, B, F, h, w, wb.noise, stream)) return rc;
+    if (int rc = forward(wb.sample, wb.timestep, skel_in, doms, cfg_on ? 2 : 1, B, F, h, w, wb.noise, stream, F_total)) return rc;
     DdimArgs d;
     d.noise = wb.noise; d.latents = latents; d.mask = mask; d.timestep_indices = ts_idx;
     d.timesteps_table = reinterpret_cast<const long long*>(sched.timesteps_table); d.alphas_cumprod = sched.alphas_cumprod;

@@ -45,6 +45,11 @@ struct Plan {
   void* arena = nullptr;
   size_t arena_bytes = 0;
   int launches = 0;
+  // frame-sharded window: this rank owns F of F_total frames per CFG half
+  int F_total = 0, rank = 0, world = 1;
+  int n3d = 0;                 // number of 3-D attention layers (K/V exchanges) per forward
+  unsigned int run_index = 0;  // forwards executed on this plan
+  unsigned int epoch0 = 0;     // exchange counter at the start of the current forward (epoch / buffer parity per layer)
   std::vector<std::function<int(cudaStream_t)>> ops;
   std::vector<int> op_kind;       // 0 gemm, 1 conv3x3, 2 attention, 3 groupnorm, 4 layernorm, 5 other
   std::vector<double> op_flops;   // executed FLOPs (incl. tile/head padding) of tensor-core ops
@@ -67,22 +72,36 @@ struct WindowBufs {  // scratch of d4d_denoise_window for one (F, h, w, cfg)
   ~WindowBufs();
 };
 
+struct Exchange {  // K/V exchange buffers in peer memory (cudaIpc), two parities
+  bool ready = false;
+  int rank = 0, world = 1;
+  size_t kv_bytes = 0;
+  void* kv[2] = {nullptr, nullptr};
+  unsigned int* flags = nullptr;  // [2][8]
+  void* peer_kv[2][8] = {};
+  unsigned int* peer_flags[8] = {};
+  unsigned int epoch_base = 0;    // monotonic across plans
+};
+
 class Model {
  public:
   Model(const d4d_config& cfg, int device);
   ~Model();
   int load_weight(const char* key, const void* data, const int64_t* shape, int ndim, int dtype);
   int finalize();
+  // F_total > F: frame-sharded window (needs exchange_open); B, F are the LOCAL batch / frames
   int forward(const bf16* sample, const long long* timestep, const bf16* skeletons, const int* domain_ids,
-              int n_domains, int B, int F, int h, int w, bf16* out, cudaStream_t stream);
+              int n_domains, int B, int F, int h, int w, bf16* out, cudaStream_t stream, int F_total = 0);
+  int exchange_alloc(size_t kv_bytes, unsigned char* handles_out /* 3 x 64 bytes */);
+  int exchange_open(int rank, int world, const unsigned char* all_handles /* world x 3 x 64 bytes */);
   int denoise_window(bf16* latents, const bf16* pixel, const bf16* plucker, const bf16* skeletons, const bf16* mask,
                      long long* ts_idx, const d4d_sched& sched, float guidance, int domain, int F, int h, int w,
-                     int num_steps, cudaStream_t stream);
+                     int num_steps, cudaStream_t stream, int F_total = 0);
   // per-kind device time (ms) of one forward, measured with CUDA events around every op
   int profile(const bf16* sample, const long long* timestep, const bf16* skeletons, const int* domain_ids, int n_domains,
               int B, int F, int h, int w, bf16* out, cudaStream_t stream, float* ms_by_kind, int* launches_by_kind,
               double* flops_by_kind);
-  int get_plan(const int* domain_ids, int n_domains, int B, int F, int h, int w, Plan** out);
+  int get_plan(const int* domain_ids, int n_domains, int B, int F, int h, int w, Plan** out, int F_total = 0);
   Plan* find_plan(int n_domains, int B, int F, int h, int w);
   const std::vector<std::string>& keys() const { return key_order_; }
   int device() const { return device_; }
@@ -113,6 +132,7 @@ class Model {
 
   std::map<std::string, std::unique_ptr<Plan>> plans_;
   std::map<std::string, std::unique_ptr<WindowBufs>> wbufs_;
+  Exchange xch_;
 
   void need(const std::string& key, int64_t numel);
   void declare_keys();

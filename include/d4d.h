@@ -141,12 +141,27 @@ int d4d_op_layernorm(const void* x, int rows, int C, float eps, const float* gam
 int d4d_op_probe_umma(const void* A, const void* B, float* D, int N, int K, int a_src, int b_major, uint32_t b_lbo,
                       uint32_t b_sbo, uint32_t b_kadv, void* stream);
 
-/* ---- multi-GPU: frame-sharded window with K/V exchange over peer memory -------
- * Rank r of `world` owns frames [r*F/world, (r+1)*F/world) of each CFG half.  `peer_kv[i]` is rank i's K/V
- * exchange buffer mapped into this process (cudaIpcOpenMemHandle; peer_kv[rank] is the local buffer),
- * `peer_flags[i]` its arrival-counter array.  See DESIGN.md "Multi-GPU". */
-int d4d_kv_exchange_bytes(d4d_handle* h, int B, int F, int height, int width, size_t* kv_bytes, size_t* flag_bytes);
-int d4d_set_peers(d4d_handle* h, int rank, int world, void* const* peer_kv, void* const* peer_flags);
+/* ---- multi-GPU: frame-sharded window with fused K/V exchange over peer memory ------------
+ * One process per GPU.  Rank r of `world` owns frames [r*F_local, (r+1)*F_local) of each CFG half (F_total = world *
+ * F_local); everything except the 3-D attention is per image.  At each 3-D block the fused-QKV GEMM epilogue stores
+ * its K|V columns directly into EVERY rank's gathered K/V buffer (peer pointers mapped with cudaIpc, NVLink stores),
+ * a system-scope flag round publishes them, and the local attention reads all F_total frames.  Two buffer parities
+ * alternate per layer so a rank may run one layer ahead of its peers.
+ *   d4d_exchange_alloc  allocates this rank's two K/V buffers (kv_bytes each) + flag array and returns three 64-byte
+ *                       cudaIpcMemHandle_t blobs (kv0, kv1, flags) to be all-gathered by the host (torch.distributed);
+ *   d4d_exchange_open   maps the peers' buffers: all_handles = [world][3][64] bytes in rank order.
+ * kv_bytes must cover 2 (CFG halves) * F_total * (h/2)*(w/2) tokens * 2*C_level1' bf16 (the largest 3-D layer). */
+int d4d_exchange_alloc(d4d_handle* h, size_t kv_bytes, unsigned char* handles_out /* [3][64] */);
+int d4d_exchange_open(d4d_handle* h, int rank, int world, const unsigned char* all_handles /* [world][3][64] */);
+/* B-2 / B-3 on a frame shard: same contracts as d4d_unet_forward / d4d_denoise_window on the LOCAL frames; every rank
+ * must call them in the same order (SPMD).  Results are bit-identical to the single-GPU call on the gathered window. */
+int d4d_unet_forward_sharded(d4d_handle* h, const void* sample, const int64_t* timestep, const void* skeletons,
+                             const int32_t* domain_ids, int n_domains, int B_local, int F_local, int F_total, int height,
+                             int width, void* out, void* stream);
+int d4d_denoise_window_sharded(d4d_handle* h, void* latents, const void* pixel_latents, const void* plucker,
+                               const void* skeletons, const void* cond_mask, int64_t* timestep_indices,
+                               const d4d_sched* sched, float guidance_scale, int domain, int F_local, int F_total,
+                               int height, int width, int num_steps, void* stream);
 
 #ifdef __cplusplus
 }
