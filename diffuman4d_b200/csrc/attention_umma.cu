@@ -11,15 +11,17 @@
 // (256 TMEM columns each: S0 S1 | P0 P1 | O).  S and P are DOUBLE-BUFFERED in TMEM so that the three stages
 //     S(j+2) = Q K^T   |   softmax(j): S -> P   |   O += P(j-1) V
 // run concurrently and the softmax warps never wait for the tensor core in steady state.
-// Warp roles (192 threads):
-//   warps 0-3  softmax: thread t owns query row t (TMEM lane t).  The 64 S values of the tile are pulled into
-//              registers with one exposed TMEM round trip and S is released at once.  P = exp2(S*scale - m) uses the
+// Warp roles (320 threads):
+//   warps 0-7  softmax: TMEM lane quarter = warp%4 (row = lane), column half = warp/4 -- the two warps of a row quarter
+//              split the 64 keys of a tile (4 softmax warps per SM sub-partition with 2 CTAs/SM hide the TMEM / barrier
+//              latencies) and exchange their half-row maxima through shared memory.  The 32 S values of a thread are
+//              pulled into registers with one TMEM round trip and S is released at once.  P = exp2(S*scale - m) uses the
 //              running max m of the previous tiles; if the row max grows by more than 8 (log2 units) O and l are
 //              rescaled before the next tile, and only if it would overflow (> 100; always for tile 0) P is recomputed
 //              from the registers with the new max.  FMNMX3 / FFMA2 / FADD2 packed math; the masked tail tile is a
 //              separate instantiation.
-//   warp  4    TMA producer: Q once, then K0 K1 K2 V0 K3 V1 ... through a ring of 8 KB*NB slots
-//   warp  5    MMA issuer:   S = Q K_j^T (SS, both K-major), O += P V_j (A = P bf16 from TMEM, B = V MN-major)
+//   warp  8    TMA producer: Q once, then K0 K1 K2 V0 K3 V1 ... through a ring of 8 KB*NB slots
+//   warp  9    MMA issuer:   S = Q K_j^T (SS, both K-major), O += P V_j (A = P bf16 from TMEM, B = V MN-major)
 #include <math.h>
 
 #include "kernels.h"
@@ -30,7 +32,7 @@ namespace {
 
 constexpr int BLOCK_Q = 128;
 constexpr int BLOCK_KV = 64;
-constexpr int ATT_THREADS = 192;
+constexpr int ATT_THREADS = 320;
 constexpr int QTILE_BYTES = 128 * 64 * 2;  // one [128 rows][64 ch] swizzled box
 constexpr int KTILE_BYTES = 64 * 64 * 2;   // one [64 keys][64 ch] swizzled box
 
@@ -40,7 +42,8 @@ struct AttCfg {
   static constexpr int SLOT_BYTES = KTILE_BYTES * NB;  // one K or V tile
   static constexpr int SLOTS = NB == 1 ? 8 : 6;
   static constexpr int Q_BYTES = QTILE_BYTES * NB;
-  static constexpr int SMEM_BYTES = Q_BYTES + SLOTS * SLOT_BYTES + 1024 + 256;
+  static constexpr int XCH_BYTES = 128 * 2 * 4 * 2 + 128 * 2 * 4 + 128;  // half-row max exchange (2 parities) + row sums + votes
+  static constexpr int SMEM_BYTES = Q_BYTES + SLOTS * SLOT_BYTES + 1024 + 256 + XCH_BYTES;
   static constexpr int TMEM_COLS = NB == 1 ? 256 : 512;
   static constexpr int COL_S = 0, COL_P = 128, COL_O = 192;  // S0 S1 (64 each) | P0 P1 (32 each) | O (D)
 };
@@ -85,6 +88,10 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8])
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]),
                "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
                : "memory");
+}
+
+__device__ __forceinline__ void pair_barrier(int q) {  // the two warps (64 threads) that share a TMEM lane quarter
+  asm volatile("bar.sync %0, 64;" ::"r"(q + 1) : "memory");
 }
 
 // Row max over 32 S columns held in registers (four independent FMNMX3 chains); kMasked: only columns < valid count
@@ -147,6 +154,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   uint64_t* p_ready = q_full + 5;  // [2]
   uint64_t* pv_done = q_full + 7;  // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_full + 9);
+  float* xmax = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);  // [2 parity][128 rows][2 halves]
+  float* xsum = xmax + 2 * 128 * 2;                                                  // [128 rows][2 halves]
+  int* xflag = reinterpret_cast<int*>(xsum + 128 * 2);                               // [2 parity][4 quarters][2 halves]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -167,19 +177,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     mbar_init(q_full, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&s_free[i], 4);
-      mbar_init(&p_ready[i], 4);
+      mbar_init(&s_free[i], 8);
+      mbar_init(&p_ready[i], 8);
       mbar_init(&pv_done[i], 1);
     }
     fence_mbar_init();
   }
-  if (warp == 5) tmem_alloc(tmem_slot, C::TMEM_COLS);
+  if (warp == 9) tmem_alloc(tmem_slot, C::TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == 4) {
+  if (warp == 8) {
     // ============================ TMA producer ============================
     if (lane == 0) {
       tma_prefetch_desc(&tmap_q);
@@ -209,7 +219,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         load_tile(true, j);
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     // ============================ MMA issuer ============================
     if (lane == 0) {
       const uint32_t idesc_qk = make_idesc_bf16(BLOCK_Q, BLOCK_KV, 0, 0);
@@ -269,18 +279,20 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     }
   } else {
     // ============================ softmax / correction / epilogue ============================
-    const int r = warp * 32 + lane;  // query row of this thread = TMEM lane
-    const uint32_t lane_sel = static_cast<uint32_t>(warp * 32) << 16;
-    const uint32_t o_tmem = tmem + C::COL_O + lane_sel;
+    const int q = warp & 3;    // TMEM lane quarter
+    const int hf = warp >> 2;  // column half: 32 of the 64 keys of a tile, 16 of the 32 packed P columns, D/2 of O
+    const int r = q * 32 + lane;  // query row of this thread = TMEM lane
+    const uint32_t lane_sel = static_cast<uint32_t>(q * 32) << 16;
+    const uint32_t o_tmem = tmem + C::COL_O + lane_sel + hf * (C::D / 2);
     const int qrow = q_tile * BLOCK_Q + r;  // row within the sequence
     const uint64_t sc2 = pack2(a.scale_log2, a.scale_log2);
-    float m = -INFINITY;     // running max (scaled log2 units) used for the exponentials of the next tile
-    float l = 0.f;           // running row sum
+    float m = -INFINITY;     // running row max (scaled log2 units) used for the exponentials of the next tile
+    float l = 0.f;           // this thread's share of the row sum (its 32 columns of every tile)
     float alpha_pend = 1.f;  // pending rescale of O and l (applied once P.V of the previous tile has landed)
 
-    auto rescale_o = [&](float alpha) {  // O[row, :] *= alpha (warp-collective; alpha is per lane/row)
+    auto rescale_o = [&](float alpha) {  // O[row, my half] *= alpha (warp-collective; alpha is per lane/row)
 #pragma unroll 1
-      for (int c = 0; c < C::D; c += 16) {
+      for (int c = 0; c < C::D / 2; c += 16) {
         uint32_t v[16];
         tmem_ld16(o_tmem + c, v);
         tmem_ld_wait();
@@ -290,28 +302,27 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       }
     };
 
-    // S(j) lives in `sv`; the TMEM loads of S(j+1) are issued at the end of iteration j (after the last use of sv) so
-    // that their latency overlaps the P-store drain and the barrier traffic of tile j (software pipelining, no extra regs)
-    uint32_t sv[64];
+    // S(j)[my 32 columns] lives in `sv`; the TMEM load of S(j+1) is issued at the end of iteration j (after the last
+    // use of sv) so that its latency overlaps the P-store drain and the barrier traffic of tile j
+    uint32_t sv[32];
     mbar_wait(&s_full[0], 0);
     tc_fence_after();
-    tmem_ld32(tmem + C::COL_S + lane_sel, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
-    tmem_ld32(tmem + C::COL_S + lane_sel + 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[32]));
+    tmem_ld32(tmem + C::COL_S + lane_sel + hf * 32, sv);
 
     for (int j = 0; j < n_tiles; ++j) {
       const int valid = min(BLOCK_KV, a.seq_kv - j * BLOCK_KV);
+      const int vcols = valid - hf * 32;  // valid columns inside my half
       const bool full = valid == BLOCK_KV;
       const int buf = j & 1;
-      const uint32_t par = (j >> 1) & 1;
-      const uint32_t p_tmem = tmem + C::COL_P + buf * 32 + lane_sel;
+      const uint32_t p_tmem = tmem + C::COL_P + buf * 32 + lane_sel + hf * 16;
       tmem_ld_wait();  // S(j) is in registers: release the buffer for Q.K(j+2)
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_free[buf]);
 
       float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-      if (full) { max32<false>(sv, mx, 32); max32<false>(sv + 32, mx, 32); }
-      else { max32<true>(sv, mx, valid); max32<true>(sv + 32, mx, valid - 32); }
+      if (full) max32<false>(sv, mx, 32);
+      else max32<true>(sv, mx, vcols);
       const float tmax = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * a.scale_log2;
 
       if (__any_sync(0xffffffffu, alpha_pend != 1.f)) {  // rescale decided at the end of tile j-1
@@ -328,13 +339,20 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       uint64_t lsum[2] = {0ull, 0ull};
       if (j > 0) {  // speculative P with the running max of the previous tiles
         const uint64_t nm2 = pack2(-m, -m);
-        if (full) { exp32<false>(sv, sc2, nm2, lsum, p_tmem, 32); exp32<false>(sv + 32, sc2, nm2, lsum, p_tmem + 16, 32); }
-        else { exp32<true>(sv, sc2, nm2, lsum, p_tmem, valid); exp32<true>(sv + 32, sc2, nm2, lsum, p_tmem + 16, valid - 32); }
+        if (full) exp32<false>(sv, sc2, nm2, lsum, p_tmem, 32);
+        else exp32<true>(sv, sc2, nm2, lsum, p_tmem, vcols);
       }
+      // the two warps of a row quarter exchange their half-row maxima (and overflow votes) through shared memory
       const bool ovf = !(tmax <= m + 100.f);  // would overflow with the old max; always true for tile 0 (m = -inf)
-      if (__any_sync(0xffffffffu, ovf)) {
+      xmax[(buf * 128 + r) * 2 + hf] = tmax;
+      const int warp_ovf = __any_sync(0xffffffffu, ovf) ? 1 : 0;
+      if (lane == 0) xflag[(buf * 4 + q) * 2 + hf] = warp_ovf;
+      pair_barrier(q);
+      const float tmax_row = fmaxf(tmax, xmax[(buf * 128 + r) * 2 + (hf ^ 1)]);
+      const bool redo = (warp_ovf | xflag[(buf * 4 + q) * 2 + (hf ^ 1)]) != 0;
+      if (redo) {
         // exact path: new max >= every logit of this tile; rescale history, recompute P from the registers
-        const float m_new = fmaxf(m, tmax);
+        const float m_new = fmaxf(m, tmax_row);
         if (j > 0) {
           const float alpha = ex2_approx(m - m_new);  // m is finite for j > 0
           if (__any_sync(0xffffffffu, alpha != 1.f)) {
@@ -348,12 +366,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         const uint64_t nm2 = pack2(-m, -m);
         lsum[0] = 0ull;
         lsum[1] = 0ull;
-        if (full) { exp32<false>(sv, sc2, nm2, lsum, p_tmem, 32); exp32<false>(sv + 32, sc2, nm2, lsum, p_tmem + 16, 32); }
-        else { exp32<true>(sv, sc2, nm2, lsum, p_tmem, valid); exp32<true>(sv + 32, sc2, nm2, lsum, p_tmem + 16, valid - 32); }
-      } else if (tmax > m + 8.f) {
+        if (full) exp32<false>(sv, sc2, nm2, lsum, p_tmem, 32);
+        else exp32<true>(sv, sc2, nm2, lsum, p_tmem, vcols);
+      } else if (tmax_row > m + 8.f) {
         // lazy rescale: this tile used the old max; fold the change into O and l before the next tile
-        alpha_pend = ex2_approx(m - tmax);
-        m = tmax;
+        alpha_pend = ex2_approx(m - tmax_row);
+        m = tmax_row;
       }
       {
         float s0, s1, s2, s3;
@@ -364,9 +382,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       if (j + 1 < n_tiles) {  // prefetch S(j+1) (ready long ago: Q.K runs two tiles ahead)
         mbar_wait(&s_full[buf ^ 1], ((j + 1) >> 1) & 1);
         tc_fence_after();
-        const uint32_t s_next = tmem + C::COL_S + (buf ^ 1) * 64 + lane_sel;
-        tmem_ld32(s_next, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
-        tmem_ld32(s_next + 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[32]));
+        tmem_ld32(tmem + C::COL_S + (buf ^ 1) * 64 + lane_sel + hf * 32, sv);
       }
       tmem_st_wait();
       tc_fence_before();
@@ -377,10 +393,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     // ---- epilogue: O / l -> bf16 -> global (a pending rescale multiplies O and l alike: skipped) ----
     mbar_wait(&pv_done[(n_tiles - 1) & 1], ((n_tiles - 1) >> 1) & 1);
     tc_fence_after();
-    const float inv_l = 1.0f / l;
-    bf16* orow = a.out + static_cast<size_t>(q_row0 + qrow) * a.ld_out + col0;
+    xsum[r * 2 + hf] = l;
+    pair_barrier(q);
+    const float inv_l = 1.0f / (l + xsum[r * 2 + (hf ^ 1)]);
+    bf16* orow = a.out + static_cast<size_t>(q_row0 + qrow) * a.ld_out + col0 + hf * (C::D / 2);
 #pragma unroll 1
-    for (int c = 0; c < C::D; c += 16) {
+    for (int c = 0; c < C::D / 2; c += 16) {
       uint32_t v[16];
       tmem_ld16(o_tmem + c, v);
       tmem_ld_wait();
@@ -403,7 +421,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == 9) {
     tc_fence_after();
     tmem_dealloc(tmem, C::TMEM_COLS);
   }

@@ -268,3 +268,30 @@ def test_full_size_properties(cuda):
     y2 = unet(x2, t, sk, doms, F, return_dict=False)[0]
     assert torch.equal(y2[:F], y[:F])                                            # negative half untouched
     assert unet.forward_launches(2, 2 * F, F, h, w) > 300
+    # temporal window W24 (12 cond + 12 target frames => 48 images): finite, deterministic, and different from 'spatial'
+    F = 24
+    x, t, sk = _inputs(cfg, F, h, w, seed=3)
+    x, t, sk = x.cuda(), t.cuda(), sk.cuda()
+    yt = unet(x, t, sk, ["temporal", "temporal"], F, return_dict=False)[0]
+    assert torch.isfinite(yt.float()).all()
+    assert torch.equal(yt, unet(x, t, sk, ["temporal", "temporal"], F, return_dict=False)[0])
+    ys = unet(x, t, sk, ["spatial", "spatial"], F, return_dict=False)[0]
+    assert (ys.float() - yt.float()).abs().max() > 0
+
+
+def test_reference_default_latent_size(cuda):
+    """The reference's default latent size (1024^2 px => 128x128 latents, DATA:27-28) with the largest window the sampler
+    builds (W24, CFG => 48 images; level-1 3-D attention over 98 304 tokens): runs, finite, cond/uncond halves independent."""
+    from diffuman4d_b200.unet import B200MultiviewUNet
+    cfg = UNetConfig.sd21(enable_pose_encoder=False, in_channels=15)
+    unet = B200MultiviewUNet(cfg, 0).load_state_dict(random_state_dict(cfg, seed=2))
+    F, h, w = 24, 128, 128
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.randn(2 * F, 15, h, w, device="cuda", generator=g).to(torch.bfloat16)
+    t = torch.randint(0, 1000, (2 * F,), device="cuda", generator=g)
+    y = unet(x, t, None, ["temporal", "temporal"], F, return_dict=False)[0]
+    assert y.shape == (2 * F, 4, h, w) and torch.isfinite(y.float()).all()
+    x2 = x.clone()
+    x2[:F] = torch.randn_like(x2[:F])
+    y2 = unet(x2, t, None, ["temporal", "temporal"], F, return_dict=False)[0]
+    assert torch.equal(y2[F:], y[F:])
