@@ -14,7 +14,7 @@ EXPORTS = [
     "d4d_num_weights", "d4d_weight_key", "d4d_unet_forward", "d4d_profile_forward", "d4d_workspace_bytes", "d4d_forward_launches",
     "d4d_denoise_window", "d4d_assemble_input", "d4d_cfg_ddim_step", "d4d_op_gemm", "d4d_op_conv3x3",
     "d4d_op_attention", "d4d_op_groupnorm", "d4d_op_layernorm", "d4d_op_probe_umma", "d4d_exchange_alloc",
-    "d4d_exchange_open", "d4d_unet_forward_sharded", "d4d_denoise_window_sharded",
+    "d4d_exchange_open", "d4d_unet_forward_sharded", "d4d_denoise_window_sharded", "d4d_microbench",
 ]
 
 
@@ -80,6 +80,8 @@ def lib() -> C.CDLL:
     l.d4d_op_groupnorm.argtypes = [vp, i32, vp, i32, i32, i32, i32, f32, f32p, f32p, i32, vp, vp]
     l.d4d_op_layernorm.argtypes = [vp, i32, i32, f32, f32p, f32p, vp, vp]
     l.d4d_op_probe_umma.argtypes = [vp, vp, vp, i32, i32, i32, i32, u32, u32, u32, vp]
+    l.d4d_microbench.argtypes = [i32, i32, i32, i32, vp, vp, vp]
+    l.d4d_microbench.restype = C.c_int
     l.d4d_exchange_alloc.argtypes = [vp, C.c_size_t, vp]
     l.d4d_exchange_open.argtypes = [vp, i32, i32, vp]
     l.d4d_unet_forward_sharded.argtypes = [vp, vp, vp, vp, C.POINTER(C.c_int32), i32, i32, i32, i32, i32, i32, vp, vp]

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_obj")
 LIB = os.path.join(HERE, "libd4d.so")
-SOURCES = ["tmap.cu", "gemm_umma.cu", "attention_umma.cu", "norm.cu", "elementwise.cu", "probe.cu", "unet.cu",
+SOURCES = ["tmap.cu", "gemm_umma.cu", "attention_umma.cu", "norm.cu", "elementwise.cu", "probe.cu", "microbench.cu", "unet.cu",
            "d4d_api.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC",

@@ -11,18 +11,17 @@
 // (256 TMEM columns each: S0 S1 | P0 P1 | O).  S and P are DOUBLE-BUFFERED in TMEM so that the three stages
 //     S(j+2) = Q K^T   |   softmax(j): S -> P   |   O += P(j-1) V
 // run concurrently and the softmax warps never wait for the tensor core in steady state.
-// Warp roles (320 threads):
-//   warps 0-7  softmax: TMEM lane quarter = warp%4 (row = lane), column half = warp/4 -- the two warps of a row quarter
-//              split the 64 keys of a tile (4 softmax warps per SM sub-partition with 2 CTAs/SM hide the TMEM / barrier
-//              latencies) and exchange their half-row maxima through shared memory.  The 32 S values of a thread are
-//              pulled into registers with one TMEM round trip and S is released at once.  P = exp2(S*scale - m) uses the
+// Warp roles (192 threads):
+//   warps 0-3  softmax: thread t owns query row t (TMEM lane t).  The 64 S values of the tile are pulled into
+//              registers with one exposed TMEM round trip and S is released at once.  P = exp2(S*scale - m) uses the
 //              running max m of the previous tiles; if the row max grows by more than 8 (log2 units) O and l are
 //              rescaled before the next tile, and only if it would overflow (> 100; always for tile 0) P is recomputed
 //              from the registers with the new max.  FMNMX3 / FFMA2 / FADD2 packed math; the masked tail tile is a
 //              separate instantiation.
-//   warp  8    TMA producer: Q once, then K0 K1 K2 V0 K3 V1 ... through a ring of 8 KB*NB slots
-//   warp  9    MMA issuer:   S = Q K_j^T (SS, both K-major), O += P V_j (A = P bf16 from TMEM, B = V MN-major)
+//   warp  4    TMA producer: Q once, then K0 K1 V0 K2 V1 K3 ... through a ring of 8 KB*NB slots
+//   warp  5    MMA issuer:   S = Q K_j^T (SS, both K-major), O += P V_j (A = P bf16 from TMEM, B = V MN-major)
 #include <math.h>
+#include <stdlib.h>
 
 #include "kernels.h"
 
@@ -32,7 +31,7 @@ namespace {
 
 constexpr int BLOCK_Q = 128;
 constexpr int BLOCK_KV = 64;
-constexpr int ATT_THREADS = 320;
+constexpr int ATT_THREADS = 192;
 constexpr int QTILE_BYTES = 128 * 64 * 2;  // one [128 rows][64 ch] swizzled box
 constexpr int KTILE_BYTES = 64 * 64 * 2;   // one [64 keys][64 ch] swizzled box
 
@@ -42,8 +41,7 @@ struct AttCfg {
   static constexpr int SLOT_BYTES = KTILE_BYTES * NB;  // one K or V tile
   static constexpr int SLOTS = NB == 1 ? 8 : 6;
   static constexpr int Q_BYTES = QTILE_BYTES * NB;
-  static constexpr int XCH_BYTES = 128 * 2 * 4 * 2 + 128 * 2 * 4 + 128;  // half-row max exchange (2 parities) + row sums + votes
-  static constexpr int SMEM_BYTES = Q_BYTES + SLOTS * SLOT_BYTES + 1024 + 256 + XCH_BYTES;
+  static constexpr int SMEM_BYTES = Q_BYTES + SLOTS * SLOT_BYTES + 1024 + 256;
   static constexpr int TMEM_COLS = NB == 1 ? 256 : 512;
   static constexpr int COL_S = 0, COL_P = 128, COL_O = 192;  // S0 S1 (64 each) | P0 P1 (32 each) | O (D)
 };
@@ -53,6 +51,7 @@ struct AttKernelArgs {
   float scale_log2;
   bf16* out;
   int ld_out;
+  int dbg;  // ablation switches for tools/ablate_attention.py (0 in production): 1 no ex2, 2 no P store, 4 no P.V, 8 no Q.K
 };
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -90,9 +89,10 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8])
                : "memory");
 }
 
-__device__ __forceinline__ void pair_barrier(int q) {  // the two warps (64 threads) that share a TMEM lane quarter
-  asm volatile("bar.sync %0, 64;" ::"r"(q + 1) : "memory");
-}
+// named barriers 1/2 ("P(j) ready", even/odd tiles): 128 softmax threads arrive, the MMA warp syncs -- a hardware barrier
+// wake-up is several times faster than an mbarrier try_wait round trip, and this hop is on the per-tile critical path
+__device__ __forceinline__ void pready_arrive(int buf) { asm volatile("bar.arrive %0, 160;" ::"r"(buf + 1) : "memory"); }
+__device__ __forceinline__ void pready_sync(int buf) { asm volatile("bar.sync %0, 160;" ::"r"(buf + 1) : "memory"); }
 
 // Row max over 32 S columns held in registers (four independent FMNMX3 chains); kMasked: only columns < valid count
 template <bool kMasked>
@@ -114,7 +114,7 @@ __device__ __forceinline__ void max32(const uint32_t* v, float (&mx)[4], int val
 // e = exp2(s*scale - m) for 32 columns -> 16 packed bf16x2 P columns in TMEM, row-sum share in two f32x2 accumulators
 template <bool kMasked>
 __device__ __forceinline__ void exp32(const uint32_t* v, uint64_t sc2, uint64_t nm2, uint64_t (&lsum)[2], uint32_t p_addr,
-                                      int valid_cols) {
+                                      int valid_cols, int dbg = 0) {
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     uint32_t pk[8];
@@ -124,7 +124,9 @@ __device__ __forceinline__ void exp32(const uint32_t* v, uint64_t sc2, uint64_t 
       const uint64_t x = fma2(pack2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), sc2, nm2);
       float x0, x1;
       unpack2(x, x0, x1);
-      float e0 = ex2_approx(x0), e1 = ex2_approx(x1);
+      float e0, e1;
+      if (dbg & 1) { e0 = x0; e1 = x1; }
+      else { e0 = ex2_approx(x0); e1 = ex2_approx(x1); }
       if (kMasked) {
         if (2 * i >= valid_cols) e0 = 0.f;
         if (2 * i + 1 >= valid_cols) e1 = 0.f;
@@ -132,7 +134,7 @@ __device__ __forceinline__ void exp32(const uint32_t* v, uint64_t sc2, uint64_t 
       pk[k] = pack_bf16x2(e0, e1);
       lsum[k & 1] = add2(lsum[k & 1], pack2(e0, e1));
     }
-    tmem_st8(p_addr + h * 8, pk);
+    if (!(dbg & 2)) tmem_st8(p_addr + h * 8, pk);
   }
 }
 
@@ -154,9 +156,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   uint64_t* p_ready = q_full + 5;  // [2]
   uint64_t* pv_done = q_full + 7;  // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_full + 9);
-  float* xmax = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);  // [2 parity][128 rows][2 halves]
-  float* xsum = xmax + 2 * 128 * 2;                                                  // [128 rows][2 halves]
-  int* xflag = reinterpret_cast<int*>(xsum + 128 * 2);                               // [2 parity][4 quarters][2 halves]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -177,19 +176,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     mbar_init(q_full, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&s_free[i], 8);
-      mbar_init(&p_ready[i], 8);
+      mbar_init(&s_free[i], 4);
+      mbar_init(&p_ready[i], 4);
       mbar_init(&pv_done[i], 1);
     }
     fence_mbar_init();
   }
-  if (warp == 9) tmem_alloc(tmem_slot, C::TMEM_COLS);
+  if (warp == 5) tmem_alloc(tmem_slot, C::TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == 8) {
+  if (warp == 4) {
     // ============================ TMA producer ============================
     if (lane == 0) {
       tma_prefetch_desc(&tmap_q);
@@ -204,95 +203,128 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       auto load_tile = [&](bool is_v, int j) {
         mbar_wait(&ring_empty[slot], phase ^ 1);
         uint8_t* dst = sRing + slot * C::SLOT_BYTES;
-        mbar_expect_tx(&ring_full[slot], C::SLOT_BYTES);
+        if (a.dbg & 16) {  // ablation: no K/V traffic
+          mbar_arrive(&ring_full[slot]);
+        } else {
+          mbar_expect_tx(&ring_full[slot], C::SLOT_BYTES);
 #pragma unroll
-        for (int nb = 0; nb < NB; ++nb)
-          tma_load_2d(dst + nb * KTILE_BYTES, is_v ? &tmap_v : &tmap_k, &ring_full[slot], col0 + nb * 64,
-                      kv_row0 + j * BLOCK_KV);
+          for (int nb = 0; nb < NB; ++nb)
+            tma_load_2d(dst + nb * KTILE_BYTES, is_v ? &tmap_v : &tmap_k, &ring_full[slot], col0 + nb * 64,
+                        kv_row0 + j * BLOCK_KV);
+        }
         if (++slot == C::SLOTS) { slot = 0; phase ^= 1; }
       };
-      // same order as the MMA warp consumes: K0 K1, then for every j: K(j+2), V(j)
+      // same order as the MMA warp consumes: K0 K1, then for every j: V(j), K(j+2)
       load_tile(false, 0);
       if (n_tiles > 1) load_tile(false, 1);
       for (int j = 0; j < n_tiles; ++j) {
-        if (j + 2 < n_tiles) load_tile(false, j + 2);
         load_tile(true, j);
+        if (j + 2 < n_tiles) load_tile(false, j + 2);
       }
     }
-  } else if (warp == 9) {
-    // ============================ MMA issuer ============================
+  } else if (warp == 5) {
+    // ============================ MMA issuer (lane 0 issues, the whole warp takes part in the named barriers) ============
+    const uint32_t idesc_qk = make_idesc_bf16(BLOCK_Q, BLOCK_KV, 0, 0);
+    const uint32_t idesc_pv = make_idesc_bf16(BLOCK_Q, C::D, 0, 1);
+    const uint32_t o_tmem = tmem + C::COL_O;
+    int slot = 0;
+    uint32_t phase = 0;
+    auto wait_ahead = [&](int k) {  // wait for the k-th next ring slot without consuming it
+      int sl = slot + k;
+      uint32_t ph = phase;
+      if (sl >= C::SLOTS) { sl -= C::SLOTS; ph ^= 1; }
+      mbar_wait(&ring_full[sl], ph);
+    };
+    auto issue_qk = [&](int j) {  // S[j&1] = Q K_j^T   (operands already waited for)
+      const uint32_t kaddr = smem_u32(sRing + slot * C::SLOT_BYTES);
+      const uint32_t s_tmem = tmem + C::COL_S + (j & 1) * 64;
+#pragma unroll
+      for (int nb = 0; nb < NB; ++nb) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t ad = make_smem_desc(smem_u32(sQ) + nb * QTILE_BYTES + k * 32, 0, 1024, 2);
+          const uint64_t bd = make_smem_desc(kaddr + nb * KTILE_BYTES + k * 32, 0, 1024, 2);
+          if (!(a.dbg & 8)) umma_ss(s_tmem, ad, bd, idesc_qk, (nb | k) != 0 ? 1u : 0u);
+        }
+      }
+    };
+    auto issue_pv = [&](int j) {  // O += P[j&1] V_j     (operands already waited for)
+      const uint32_t vaddr = smem_u32(sRing + slot * C::SLOT_BYTES);
+      const uint32_t p_tmem = tmem + C::COL_P + (j & 1) * 32;
+#pragma unroll
+      for (int k = 0; k < BLOCK_KV / 16; ++k) {
+        // V tile = NB boxes of [64 keys][64 d] (d contiguous): MN-major B operand.
+        // 16 keys = two 8-row swizzle atoms = 2048 bytes; SBO = 1024 (next 8 keys), LBO = next 64-wide d block
+        const uint64_t bd = make_smem_desc(vaddr + k * 2048, KTILE_BYTES, 1024, 2);
+        if (!(a.dbg & 4)) umma_ts(o_tmem, p_tmem + k * 8, bd, idesc_pv, (j | k) != 0 ? 1u : 0u);
+      }
+    };
+    auto advance = [&]() {
+      const int used = slot;
+      if (++slot == C::SLOTS) { slot = 0; phase ^= 1; }
+      return used;
+    };
     if (lane == 0) {
-      const uint32_t idesc_qk = make_idesc_bf16(BLOCK_Q, BLOCK_KV, 0, 0);
-      const uint32_t idesc_pv = make_idesc_bf16(BLOCK_Q, C::D, 0, 1);
-      const uint32_t o_tmem = tmem + C::COL_O;
-      int slot = 0;
-      uint32_t phase = 0;
-      auto issue_qk = [&](int j) {  // S[j&1] = Q K_j^T
-        mbar_wait(&ring_full[slot], phase);
-        tc_fence_after();
-        const uint32_t kaddr = smem_u32(sRing + slot * C::SLOT_BYTES);
-        const uint32_t s_tmem = tmem + C::COL_S + (j & 1) * 64;
-#pragma unroll
-        for (int nb = 0; nb < NB; ++nb) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t ad = make_smem_desc(smem_u32(sQ) + nb * QTILE_BYTES + k * 32, 0, 1024, 2);
-            const uint64_t bd = make_smem_desc(kaddr + nb * KTILE_BYTES + k * 32, 0, 1024, 2);
-            umma_ss(s_tmem, ad, bd, idesc_qk, (nb | k) != 0 ? 1u : 0u);
-          }
-        }
-        umma_commit(&ring_empty[slot]);
-        umma_commit(&s_full[j & 1]);
-        if (++slot == C::SLOTS) { slot = 0; phase ^= 1; }
-      };
-      auto issue_pv = [&](int j) {  // O += P[j&1] V_j
-        mbar_wait(&ring_full[slot], phase);
-        tc_fence_after();
-        const uint32_t vaddr = smem_u32(sRing + slot * C::SLOT_BYTES);
-        const uint32_t p_tmem = tmem + C::COL_P + (j & 1) * 32;
-#pragma unroll
-        for (int k = 0; k < BLOCK_KV / 16; ++k) {
-          // V tile = NB boxes of [64 keys][64 d] (d contiguous): MN-major B operand.
-          // 16 keys = two 8-row swizzle atoms = 2048 bytes; SBO = 1024 (next 8 keys), LBO = next 64-wide d block
-          const uint64_t bd = make_smem_desc(vaddr + k * 2048, KTILE_BYTES, 1024, 2);
-          umma_ts(o_tmem, p_tmem + k * 8, bd, idesc_pv, (j | k) != 0 ? 1u : 0u);
-        }
-        umma_commit(&ring_empty[slot]);
-        umma_commit(&pv_done[j & 1]);
-        if (++slot == C::SLOTS) { slot = 0; phase ^= 1; }
-      };
       mbar_wait(q_full, 0);
+      wait_ahead(0);
       tc_fence_after();
       issue_qk(0);
-      if (n_tiles > 1) issue_qk(1);
-      for (int j = 0; j < n_tiles; ++j) {
-        const uint32_t par = (j >> 1) & 1;
-        if (j + 2 < n_tiles) {
-          mbar_wait(&s_free[j & 1], par);  // every softmax thread holds S(j) in registers
-          tc_fence_after();
-          issue_qk(j + 2);
-        }
-        mbar_wait(&p_ready[j & 1], par);
+      umma_commit(&s_full[0]);
+      umma_commit(&ring_empty[advance()]);
+      if (n_tiles > 1) {
+        wait_ahead(0);
+        tc_fence_after();
+        issue_qk(1);
+        umma_commit(&s_full[1]);
+        umma_commit(&ring_empty[advance()]);
+      }
+    }
+    slot = __shfl_sync(0xffffffffu, slot, 0);
+    phase = __shfl_sync(0xffffffffu, phase, 0);
+    for (int j = 0; j < n_tiles; ++j) {
+      if (lane == 0) {  // operands of this iteration, waited for BEFORE the critical-path barrier
+        wait_ahead(0);                      // V(j)
+        if (j + 2 < n_tiles) wait_ahead(1);  // K(j+2)
+      }
+      __syncwarp();
+      // P(j) ready also means S(j) has been consumed.  P.V(j) is issued BEFORE Q.K(j+2): tcgen05.commit covers all
+      // earlier MMAs of this thread, so s_full(j+2) doubles as "P.V(j) done" and the softmax warps need no separate
+      // wait before reusing the P buffer two tiles later.
+      pready_sync(j & 1);
+      if (lane == 0) {
         tc_fence_after();
         issue_pv(j);
+        const int v_slot = advance();
+        if (j + 2 < n_tiles) {
+          issue_qk(j + 2);
+          // the commit the softmax warps are waiting for goes FIRST (each tcgen05.commit takes a few hundred cycles to
+          // issue and they serialise); it covers P.V(j) as well as Q.K(j+2)
+          umma_commit(&s_full[j & 1]);
+          umma_commit(&pv_done[j & 1]);
+          umma_commit(&ring_empty[v_slot]);
+          umma_commit(&ring_empty[advance()]);
+        } else {
+          umma_commit(&pv_done[j & 1]);
+          umma_commit(&ring_empty[v_slot]);
+        }
       }
+      slot = __shfl_sync(0xffffffffu, slot, 0);
+      phase = __shfl_sync(0xffffffffu, phase, 0);
     }
   } else {
     // ============================ softmax / correction / epilogue ============================
-    const int q = warp & 3;    // TMEM lane quarter
-    const int hf = warp >> 2;  // column half: 32 of the 64 keys of a tile, 16 of the 32 packed P columns, D/2 of O
-    const int r = q * 32 + lane;  // query row of this thread = TMEM lane
-    const uint32_t lane_sel = static_cast<uint32_t>(q * 32) << 16;
-    const uint32_t o_tmem = tmem + C::COL_O + lane_sel + hf * (C::D / 2);
+    const int r = warp * 32 + lane;  // query row of this thread = TMEM lane
+    const uint32_t lane_sel = static_cast<uint32_t>(warp * 32) << 16;
+    const uint32_t o_tmem = tmem + C::COL_O + lane_sel;
     const int qrow = q_tile * BLOCK_Q + r;  // row within the sequence
     const uint64_t sc2 = pack2(a.scale_log2, a.scale_log2);
-    float m = -INFINITY;     // running row max (scaled log2 units) used for the exponentials of the next tile
-    float l = 0.f;           // this thread's share of the row sum (its 32 columns of every tile)
+    float m = -INFINITY;     // running max (scaled log2 units) used for the exponentials of the next tile
+    float l = 0.f;           // running row sum
     float alpha_pend = 1.f;  // pending rescale of O and l (applied once P.V of the previous tile has landed)
 
-    auto rescale_o = [&](float alpha) {  // O[row, my half] *= alpha (warp-collective; alpha is per lane/row)
+    auto rescale_o = [&](float alpha) {  // O[row, :] *= alpha (warp-collective; alpha is per lane/row)
 #pragma unroll 1
-      for (int c = 0; c < C::D / 2; c += 16) {
+      for (int c = 0; c < C::D; c += 16) {
         uint32_t v[16];
         tmem_ld16(o_tmem + c, v);
         tmem_ld_wait();
@@ -302,27 +334,34 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       }
     };
 
-    // S(j)[my 32 columns] lives in `sv`; the TMEM load of S(j+1) is issued at the end of iteration j (after the last
-    // use of sv) so that its latency overlaps the P-store drain and the barrier traffic of tile j
-    uint32_t sv[32];
+    // S(j) lives in `sv`; the TMEM loads of S(j+1) are issued at the end of iteration j (after the last use of sv) so
+    // that their latency overlaps the P-store drain and the barrier traffic of tile j (software pipelining, no extra regs)
+    uint32_t sv[64];
     mbar_wait(&s_full[0], 0);
     tc_fence_after();
-    tmem_ld32(tmem + C::COL_S + lane_sel + hf * 32, sv);
+    tmem_ld32(tmem + C::COL_S + lane_sel, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
+    tmem_ld32(tmem + C::COL_S + lane_sel + 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[32]));
 
     for (int j = 0; j < n_tiles; ++j) {
       const int valid = min(BLOCK_KV, a.seq_kv - j * BLOCK_KV);
-      const int vcols = valid - hf * 32;  // valid columns inside my half
       const bool full = valid == BLOCK_KV;
       const int buf = j & 1;
-      const uint32_t p_tmem = tmem + C::COL_P + buf * 32 + lane_sel + hf * 16;
-      tmem_ld_wait();  // S(j) is in registers: release the buffer for Q.K(j+2)
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s_free[buf]);
+      const uint32_t par = (j >> 1) & 1;
+      const uint32_t p_tmem = tmem + C::COL_P + buf * 32 + lane_sel;
+      tmem_ld_wait();  // S(j) is in registers
 
       float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-      if (full) max32<false>(sv, mx, 32);
-      else max32<true>(sv, mx, vcols);
+      if (a.dbg & 64) {  // ablation: barriers only
+        tc_fence_before();
+        pready_arrive(buf);
+        if (j + 1 < n_tiles) {
+          mbar_wait(&s_full[buf ^ 1], ((j + 1) >> 1) & 1);
+          tc_fence_after();
+        }
+        continue;
+      }
+      if (full) { max32<false>(sv, mx, 32); max32<false>(sv + 32, mx, 32); }
+      else { max32<true>(sv, mx, valid); max32<true>(sv + 32, mx, valid - 32); }
       const float tmax = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * a.scale_log2;
 
       if (__any_sync(0xffffffffu, alpha_pend != 1.f)) {  // rescale decided at the end of tile j-1
@@ -332,27 +371,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         l *= alpha_pend;
         alpha_pend = 1.f;
       }
-      if (j >= 2) {  // P[buf] was last read by P.V(j-2): long finished in steady state
-        mbar_wait(&pv_done[buf], ((j - 2) >> 1) & 1);
-        tc_fence_after();
-      }
+      // P[buf] was last read by P.V(j-2), which completed before s_full(j) fired (MMA issue order + commit semantics)
       uint64_t lsum[2] = {0ull, 0ull};
       if (j > 0) {  // speculative P with the running max of the previous tiles
         const uint64_t nm2 = pack2(-m, -m);
-        if (full) exp32<false>(sv, sc2, nm2, lsum, p_tmem, 32);
-        else exp32<true>(sv, sc2, nm2, lsum, p_tmem, vcols);
+        if (full) { exp32<false>(sv, sc2, nm2, lsum, p_tmem, 32, a.dbg); exp32<false>(sv + 32, sc2, nm2, lsum, p_tmem + 16, 32, a.dbg); }
+        else { exp32<true>(sv, sc2, nm2, lsum, p_tmem, valid); exp32<true>(sv + 32, sc2, nm2, lsum, p_tmem + 16, valid - 32); }
       }
-      // the two warps of a row quarter exchange their half-row maxima (and overflow votes) through shared memory
       const bool ovf = !(tmax <= m + 100.f);  // would overflow with the old max; always true for tile 0 (m = -inf)
-      xmax[(buf * 128 + r) * 2 + hf] = tmax;
-      const int warp_ovf = __any_sync(0xffffffffu, ovf) ? 1 : 0;
-      if (lane == 0) xflag[(buf * 4 + q) * 2 + hf] = warp_ovf;
-      pair_barrier(q);
-      const float tmax_row = fmaxf(tmax, xmax[(buf * 128 + r) * 2 + (hf ^ 1)]);
-      const bool redo = (warp_ovf | xflag[(buf * 4 + q) * 2 + (hf ^ 1)]) != 0;
-      if (redo) {
+      if (__any_sync(0xffffffffu, ovf)) {
         // exact path: new max >= every logit of this tile; rescale history, recompute P from the registers
-        const float m_new = fmaxf(m, tmax_row);
+        const float m_new = fmaxf(m, tmax);
         if (j > 0) {
           const float alpha = ex2_approx(m - m_new);  // m is finite for j > 0
           if (__any_sync(0xffffffffu, alpha != 1.f)) {
@@ -366,12 +395,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         const uint64_t nm2 = pack2(-m, -m);
         lsum[0] = 0ull;
         lsum[1] = 0ull;
-        if (full) exp32<false>(sv, sc2, nm2, lsum, p_tmem, 32);
-        else exp32<true>(sv, sc2, nm2, lsum, p_tmem, vcols);
-      } else if (tmax_row > m + 8.f) {
+        if (full) { exp32<false>(sv, sc2, nm2, lsum, p_tmem, 32, a.dbg); exp32<false>(sv + 32, sc2, nm2, lsum, p_tmem + 16, 32, a.dbg); }
+        else { exp32<true>(sv, sc2, nm2, lsum, p_tmem, valid); exp32<true>(sv + 32, sc2, nm2, lsum, p_tmem + 16, valid - 32); }
+      } else if (tmax > m + 8.f) {
         // lazy rescale: this tile used the old max; fold the change into O and l before the next tile
-        alpha_pend = ex2_approx(m - tmax_row);
-        m = tmax_row;
+        alpha_pend = ex2_approx(m - tmax);
+        m = tmax;
       }
       {
         float s0, s1, s2, s3;
@@ -379,26 +408,27 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         unpack2(lsum[1], s2, s3);
         l += (s0 + s1) + (s2 + s3);
       }
-      if (j + 1 < n_tiles) {  // prefetch S(j+1) (ready long ago: Q.K runs two tiles ahead)
-        mbar_wait(&s_full[buf ^ 1], ((j + 1) >> 1) & 1);
-        tc_fence_after();
-        tmem_ld32(tmem + C::COL_S + (buf ^ 1) * 64 + lane_sel + hf * 32, sv);
-      }
       tmem_st_wait();
       tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&p_ready[buf]);
+      pready_arrive(buf);  // hand P(j) to the MMA warp FIRST: the wait below must not delay P.V(j) / Q.K(j+2)
+      if (j + 1 < n_tiles) {  // then fetch S(j+1) (Q.K runs two tiles ahead); its latency overlaps the hand-off
+        mbar_wait(&s_full[buf ^ 1], ((j + 1) >> 1) & 1);
+        tc_fence_after();
+        const uint32_t s_next = tmem + C::COL_S + (buf ^ 1) * 64 + lane_sel;
+        if (!(a.dbg & 32)) {
+          tmem_ld32(s_next, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
+          tmem_ld32(s_next + 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[32]));
+        }
+      }
     }
     tmem_ld_wait();
     // ---- epilogue: O / l -> bf16 -> global (a pending rescale multiplies O and l alike: skipped) ----
     mbar_wait(&pv_done[(n_tiles - 1) & 1], ((n_tiles - 1) >> 1) & 1);
     tc_fence_after();
-    xsum[r * 2 + hf] = l;
-    pair_barrier(q);
-    const float inv_l = 1.0f / (l + xsum[r * 2 + (hf ^ 1)]);
-    bf16* orow = a.out + static_cast<size_t>(q_row0 + qrow) * a.ld_out + col0 + hf * (C::D / 2);
+    const float inv_l = 1.0f / l;
+    bf16* orow = a.out + static_cast<size_t>(q_row0 + qrow) * a.ld_out + col0;
 #pragma unroll 1
-    for (int c = 0; c < C::D / 2; c += 16) {
+    for (int c = 0; c < C::D; c += 16) {
       uint32_t v[16];
       tmem_ld16(o_tmem + c, v);
       tmem_ld_wait();
@@ -421,7 +451,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) {
+  if (warp == 5) {
     tc_fence_after();
     tmem_dealloc(tmem, C::TMEM_COLS);
   }
@@ -440,6 +470,14 @@ int launch_attn(const AttnLaunch& L, cudaStream_t stream) {
   a.scale_log2 = L.d.scale * 1.4426950408889634f;
   a.out = L.d.out;
   a.ld_out = L.d.ld_out;
+  {
+    static int dbg = -1;
+    if (dbg < 0) {
+      const char* e = getenv("D4D_ATTN_ABLATE");
+      dbg = e ? atoi(e) : 0;
+    }
+    a.dbg = dbg;
+  }
   dim3 grid(L.grid_x, L.grid_y);
   attn_fwd_kernel<NB><<<grid, ATT_THREADS, C::SMEM_BYTES, stream>>>(L.tmap_q, L.tmap_k, L.tmap_v, a);
   D4D_CUDA_OK(cudaGetLastError());

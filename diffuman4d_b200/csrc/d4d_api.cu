@@ -305,6 +305,13 @@ int d4d_op_probe_umma(const void* A, const void* B, float* D, int N, int K, int 
   D4D_API_END
 }
 
+int d4d_microbench(int kind, int warps, int iters, int blocks, uint64_t* cycles_dev, float* sink_dev, void* stream) {
+  D4D_API_BEGIN
+  return d4d::microbench_run(kind, warps, iters, blocks, reinterpret_cast<unsigned long long*>(cycles_dev), sink_dev,
+                             static_cast<cudaStream_t>(stream));
+  D4D_API_END
+}
+
 int d4d_unet_forward_sharded(d4d_handle* h, const void* sample, const int64_t* timestep, const void* skeletons,
                              const int32_t* domain_ids, int n_domains, int B_local, int F_local, int F_total, int height,
                              int width, void* out, void* stream) {

@@ -232,6 +232,23 @@ __global__ void assemble_kernel(const AssembleArgs a, int Cin) {
   }
 }
 
+// images 0..F-1 <- small image 0 ; images F..2F-1 <- small images 1..F   (per_img elements each, multiple of 8)
+__global__ void broadcast_neg_images_kernel(const bf16* __restrict__ small, long long per_img8, int F, bf16* __restrict__ full) {
+  const long long total = per_img8 * 2 * F;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long img = i / per_img8, off = i - img * per_img8;
+    const long long src = img < F ? 0 : img - F + 1;
+    reinterpret_cast<uint4*>(full)[i] = __ldg(reinterpret_cast<const uint4*>(small) + src * per_img8 + off);
+  }
+}
+__global__ void fill_bf16_kernel(bf16* __restrict__ p, long long n, float v) {
+  const bf16 b = __float2bfloat16_rn(v);
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    p[i] = b;
+}
+
 __global__ void cfg_skeleton_kernel(const bf16* __restrict__ skel, long long per_frame, int F, bf16* __restrict__ out) {
   const long long total = per_frame * F;
   const bf16 mone = __float2bfloat16_rn(-1.f);
@@ -427,6 +444,18 @@ int assemble_input_run(const AssembleArgs& a, cudaStream_t stream) {
   const int hw = a.h * a.w;
   dim3 grid(min(64, blocks_for(hw, 256)), a.F);
   assemble_kernel<<<grid, 256, 0, stream>>>(a, Cin);
+  D4D_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int broadcast_neg_images_run(const bf16* small, long long per_img, int F, bf16* full, cudaStream_t stream) {
+  D4D_REQUIRE(per_img % 8 == 0 && F > 0, "broadcast_neg_images arguments");
+  broadcast_neg_images_kernel<<<148 * 8, 256, 0, stream>>>(small, per_img / 8, F, full);
+  D4D_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+int fill_bf16_run(bf16* p, long long n, float v, cudaStream_t stream) {
+  fill_bf16_kernel<<<148 * 4, 256, 0, stream>>>(p, n, v);
   D4D_CUDA_OK(cudaGetLastError());
   return 0;
 }

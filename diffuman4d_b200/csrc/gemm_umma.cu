@@ -357,7 +357,26 @@ int gemm_prepare(const GemmDesc& d, GemmLaunch* L) {
   D4D_REQUIRE(d.out != nullptr && d.A != nullptr && d.Wt != nullptr, "null operand");
   GemmKernelArgs& a = L->args;
   memset(&a, 0, sizeof(a));
-  const int bn = d.block_n > 0 ? d.block_n : gemm_pick_block_n(d.N, d.geglu ? 32 : 16);
+  int bn = d.block_n;
+  if (bn <= 0) {
+    // widest tile that divides N, unless a narrower one wastes fewer SM-waves (persistent grid = #SMs):
+    // cost ~ waves * (block_n + fixed per-tile work)
+    int dev0 = 0, sms0 = 148;
+    cudaGetDevice(&dev0);
+    cudaDeviceGetAttribute(&sms0, cudaDevAttrMultiProcessorCount, dev0);
+    const long long rows = d.conv ? static_cast<long long>(d.n_img) * d.H * d.W : d.M;
+    const long long m_tiles_est = (rows + BLOCK_M - 1) / BLOCK_M;
+    const int mult = d.geglu ? 32 : 16;
+    bn = gemm_pick_block_n(d.N, mult);
+    long long best_cost = -1;
+    for (int c = mult; c <= 256; c += mult) {
+      if (d.N % c != 0 || (c < 64 && c != bn)) continue;
+      const long long tiles = m_tiles_est * (d.N / c);
+      const long long waves = (tiles + sms0 - 1) / sms0;
+      const long long cost = waves * (c + 48);
+      if (best_cost < 0 || cost < best_cost || (cost == best_cost && c > bn)) { best_cost = cost; bn = c; }
+    }
+  }
   D4D_REQUIRE(bn >= 16 && d.N % bn == 0 && bn % (d.geglu ? 32 : 16) == 0, "no valid block_n");
   a.block_n = bn;
   a.n_tiles = d.N / bn;

@@ -186,6 +186,9 @@ struct KvFlagArgs {
 int kv_signal_run(const KvFlagArgs& a, cudaStream_t stream);
 int kv_wait_run(const KvFlagArgs& a, cudaStream_t stream);
 
+// device microbenchmarks (microbench.cu)
+int microbench_run(int kind, int warps, int iters, int blocks, unsigned long long* cycles_dev, float* sink_dev, cudaStream_t s);
+
 // UMMA operand-encoding probe (probe.cu)
 int probe_umma_run(const bf16* A, const bf16* B, float* D, int N, int K, int a_src, int b_major, uint32_t b_lbo,
                    uint32_t b_sbo, uint32_t b_kadv, cudaStream_t stream);

@@ -1,0 +1,127 @@
+// Device microbenchmarks used to size the attention kernel (exported as d4d_microbench, test/bring-up utility):
+// per-SM throughput of tcgen05.ld / tcgen05.st (TMEM <-> registers), MUFU.EX2 and the bf16 pack conversion.
+#include "kernels.h"
+
+namespace d4d {
+namespace {
+
+// kind 0: tcgen05.ld 32x32b.x32   1: tcgen05.ld 32x32b.x16   2: tcgen05.st 32x32b.x16   3: ex2.approx   4: cvt.bf16x2
+__global__ void microbench_kernel(int kind, int iters, unsigned long long* cycles, float* sink) {
+  __shared__ uint32_t slot;
+  const int warp = threadIdx.x >> 5;
+  if (warp == 0) tmem_alloc(&slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = slot;
+  const uint32_t taddr = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16) + ((warp >> 2) & 3) * 64;
+  float acc = 0.f;
+  __syncthreads();
+  const unsigned long long t0 = clock64();
+  if (kind == 0) {
+    for (int i = 0; i < iters; ++i) {
+      uint32_t v[32];
+      tmem_ld32(taddr + (i & 1) * 32, v);
+      tmem_ld_wait();
+      acc += __uint_as_float(v[0] ^ v[13] ^ v[31]);
+    }
+  } else if (kind == 1) {
+    for (int i = 0; i < iters; ++i) {
+      uint32_t v[16];
+      tmem_ld16(taddr + (i & 3) * 16, v);
+      tmem_ld_wait();
+      acc += __uint_as_float(v[0] ^ v[7] ^ v[15]);
+    }
+  } else if (kind == 5) {
+    for (int i = 0; i < iters; ++i) {
+      uint32_t v[16], w[16];
+      tmem_ld16(taddr, v);
+      tmem_ld16(taddr + 16, w);
+      tmem_ld_wait();
+      acc += __uint_as_float(v[0] ^ v[15] ^ w[0] ^ w[15]);
+    }
+  } else if (kind == 6) {
+    for (int i = 0; i < iters; ++i) {
+      uint32_t v[32], w[32];
+      tmem_ld32(taddr, v);
+      tmem_ld32(taddr + 32, w);
+      tmem_ld_wait();
+      acc += __uint_as_float(v[0] ^ v[31] ^ w[0] ^ w[31]);
+    }
+  } else if (kind == 7 || kind == 8) {
+    // latency of tcgen05.commit -> mbarrier completion -> try_wait return (kind 8: preceded by one 128x64x16 MMA)
+    __shared__ uint64_t bar;
+    __shared__ __align__(1024) uint8_t tile[2][128 * 128];
+    if (threadIdx.x == 0) {
+      mbar_init(&bar, 1);
+      fence_mbar_init();
+      uint32_t ph = 0;
+      const uint32_t idesc = make_idesc_bf16(128, 64, 0, 0);
+      for (int i = 0; i < iters; ++i) {
+        if (kind == 8) {
+          const uint64_t ad = make_smem_desc(smem_u32(tile[0]), 0, 1024, 2);
+          const uint64_t bd = make_smem_desc(smem_u32(tile[1]), 0, 1024, 2);
+          umma_ss(tmem, ad, bd, idesc, 0);
+        }
+        umma_commit(&bar);
+        mbar_wait(&bar, ph);
+        ph ^= 1;
+      }
+    }
+  } else if (kind == 2) {
+    uint32_t v[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) v[k] = threadIdx.x + k;
+    for (int i = 0; i < iters; ++i) {
+      tmem_st16(taddr + (i & 3) * 16, v);
+      v[0] += 1;
+    }
+    tmem_st_wait();
+  } else if (kind == 3) {
+    float x[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x[k] = -0.001f * (threadIdx.x + k);
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(x[k]));
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc += x[k];
+  } else {
+    float x[8];
+    uint32_t u = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x[k] = 0.5f * (threadIdx.x + k);
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+      for (int k = 0; k < 8; k += 2) {
+        uint32_t p;
+        asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p) : "f"(x[k + 1]), "f"(x[k]));
+        u ^= p;
+        x[k] += 1.0f;
+      }
+    }
+    acc += __uint_as_float(u);
+  }
+  __syncthreads();
+  const unsigned long long t1 = clock64();
+  if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+  if (acc == 12345.678f) sink[0] = acc;
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+}  // namespace
+
+int microbench_run(int kind, int warps, int iters, int blocks, unsigned long long* cycles_dev, float* sink_dev, cudaStream_t s) {
+  D4D_REQUIRE(kind >= 0 && kind <= 8 && warps >= 1 && warps <= 16 && iters > 0 && blocks > 0, "microbench arguments");
+  microbench_kernel<<<blocks, warps * 32, 0, s>>>(kind, iters, cycles_dev, sink_dev);
+  D4D_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace d4d

@@ -16,6 +16,8 @@
 namespace d4d {
 
 int silu_run(const bf16* x, long long n, bf16* out, cudaStream_t stream);
+int broadcast_neg_images_run(const bf16* small, long long per_img, int F, bf16* full, cudaStream_t stream);
+int fill_bf16_run(bf16* p, long long n, float v, cudaStream_t stream);
 
 namespace {
 
@@ -723,11 +725,12 @@ class PlanBuilder {
     return {out, C, in.H, in.W};
   }
 
-  Act conv3x3(const LinW& w, Act in, int act = 0) {
-    const int M = p_.B * in.H * in.W;
+  Act conv3x3(const LinW& w, Act in, int act = 0, int n_img = 0) {
+    if (n_img <= 0) n_img = p_.B;
+    const int M = n_img * in.H * in.W;
     bf16* out = alloc(static_cast<size_t>(M) * w.out);
     GemmDesc d;
-    d.conv = 1; d.A = in.p; d.n_img = p_.B; d.H = in.H; d.W = in.W; d.Cin = in.C;
+    d.conv = 1; d.A = in.p; d.n_img = n_img; d.H = in.H; d.W = in.W; d.Cin = in.C;
     d.Wt = w.w; d.N = w.out; d.bias = w.b; d.out = out; d.ldo = w.out; d.act = act;
     gemm(d);
     return {out, w.out, in.H, in.W};
@@ -804,44 +807,57 @@ class PlanBuilder {
     bf16* pose_emb = nullptr;
     if (cfg.enable_pose_encoder) {
       const int Hs = 8 * h, Ws = 8 * w;
+      // pose_shared_neg: the skeleton batch is [1 constant CFG-negative image | F positive images] instead of 2F images
+      // (pipeline_diffuman4d.py:349-356 makes every negative skeleton the same all(-1) image); its embedding is computed
+      // once per forward and broadcast to the F negative images below
+      const int PB = p_.pose_shared_neg ? F + 1 : B;
+      const int PM0 = PB * h * w;
       const PoseW& pw = m.pose_;
-      bf16* a0 = alloc(static_cast<size_t>(B) * Hs * Ws * 3);
-      op([=](cudaStream_t s) { return direct_conv_run(pl->skeletons, 1, B, 3, Hs, Ws, pw.conv[0].w, pw.conv[0].b, 3, 3, 1, 1, 1.f, a0, s); });
-      bf16* a1 = alloc(static_cast<size_t>(B) * (Hs / 2) * (Ws / 2) * 16);
-      op([=](cudaStream_t s) { return direct_conv_run(a0, 0, B, 3, Hs, Ws, pw.conv[1].w, pw.conv[1].b, 16, 4, 2, 1, 1.f, a1, s); });
+      bf16* a0 = alloc(static_cast<size_t>(PB) * Hs * Ws * 3);
+      op([=](cudaStream_t s) { return direct_conv_run(pl->skeletons, 1, PB, 3, Hs, Ws, pw.conv[0].w, pw.conv[0].b, 3, 3, 1, 1, 1.f, a0, s); });
+      bf16* a1 = alloc(static_cast<size_t>(PB) * (Hs / 2) * (Ws / 2) * 16);
+      op([=](cudaStream_t s) { return direct_conv_run(a0, 0, PB, 3, Hs, Ws, pw.conv[1].w, pw.conv[1].b, 16, 4, 2, 1, 1.f, a1, s); });
       release(a0);
-      bf16* a2 = alloc(static_cast<size_t>(B) * (Hs / 2) * (Ws / 2) * 16);
-      op([=](cudaStream_t s) { return direct_conv_run(a1, 0, B, 16, Hs / 2, Ws / 2, pw.conv[2].w, pw.conv[2].b, 16, 3, 1, 1, 1.f, a2, s); });
+      bf16* a2 = alloc(static_cast<size_t>(PB) * (Hs / 2) * (Ws / 2) * 16);
+      op([=](cudaStream_t s) { return direct_conv_run(a1, 0, PB, 16, Hs / 2, Ws / 2, pw.conv[2].w, pw.conv[2].b, 16, 3, 1, 1, 1.f, a2, s); });
       release(a1);
-      bf16* a3 = alloc(static_cast<size_t>(B) * (Hs / 4) * (Ws / 4) * 32);
-      op([=](cudaStream_t s) { return direct_conv_run(a2, 0, B, 16, Hs / 2, Ws / 2, pw.conv[3].w, pw.conv[3].b, 32, 4, 2, 1, 1.f, a3, s); });
+      bf16* a3 = alloc(static_cast<size_t>(PB) * (Hs / 4) * (Ws / 4) * 32);
+      op([=](cudaStream_t s) { return direct_conv_run(a2, 0, PB, 16, Hs / 2, Ws / 2, pw.conv[3].w, pw.conv[3].b, 32, 4, 2, 1, 1.f, a3, s); });
       release(a2);
-      bf16* a4 = alloc(static_cast<size_t>(B) * (Hs / 4) * (Ws / 4) * 32);
-      op([=](cudaStream_t s) { return direct_conv_run(a3, 0, B, 32, Hs / 4, Ws / 4, pw.conv[4].w, pw.conv[4].b, 32, 3, 1, 1, 1.f, a4, s); });
+      bf16* a4 = alloc(static_cast<size_t>(PB) * (Hs / 4) * (Ws / 4) * 32);
+      op([=](cudaStream_t s) { return direct_conv_run(a3, 0, PB, 32, Hs / 4, Ws / 4, pw.conv[4].w, pw.conv[4].b, 32, 3, 1, 1, 1.f, a4, s); });
       release(a3);
-      bf16* col = alloc(static_cast<size_t>(M0) * 512);
-      op([=](cudaStream_t s) { return im2col_nhwc_run(a4, B, Hs / 4, Ws / 4, 32, 4, 2, col, s); });
+      bf16* col = alloc(static_cast<size_t>(PM0) * 512);
+      op([=](cudaStream_t s) { return im2col_nhwc_run(a4, PB, Hs / 4, Ws / 4, 32, 4, 2, col, s); });
       release(a4);
-      bf16* a5 = alloc(static_cast<size_t>(M0) * 64);
+      bf16* a5 = alloc(static_cast<size_t>(PM0) * 64);
       {
         GemmDesc d;
-        d.A = col; d.lda = 512; d.K1 = 512; d.Wt = pw.conv[5].w; d.M = M0; d.N = 64; d.bias = pw.conv[5].b; d.act = 1; d.out = a5; d.ldo = 64;
+        d.A = col; d.lda = 512; d.K1 = 512; d.Wt = pw.conv[5].w; d.M = PM0; d.N = 64; d.bias = pw.conv[5].b; d.act = 1; d.out = a5; d.ldo = 64;
         gemm(d);
       }
       release(col);
       Act x5{a5, 64, h, w};
-      Act x6 = conv3x3(pw.conv[6], x5, 1);
+      Act x6 = conv3x3(pw.conv[6], x5, 1, PB);
       release(a5);
-      Act x7 = conv3x3(pw.conv[7], x6, 1);
+      Act x7 = conv3x3(pw.conv[7], x6, 1, PB);
       release(x6.p);
-      pose_emb = alloc(static_cast<size_t>(M0) * C0);
+      pose_emb = alloc(static_cast<size_t>(PM0) * C0);
       {
         GemmDesc d;
-        d.A = x7.p; d.lda = 128; d.K1 = 128; d.Wt = pw.proj.w; d.M = M0; d.N = C0; d.bias = pw.proj.b; d.out_scale = pw.scale;
+        d.A = x7.p; d.lda = 128; d.K1 = 128; d.Wt = pw.proj.w; d.M = PM0; d.N = C0; d.bias = pw.proj.b; d.out_scale = pw.scale;
         d.out = pose_emb; d.ldo = C0;
         gemm(d);
       }
       release(x7.p);
+      if (p_.pose_shared_neg) {  // broadcast: images 0..F-1 <- embedding 0, images F..2F-1 <- embeddings 1..F
+        bf16* full = alloc(static_cast<size_t>(M0) * C0);
+        bf16* small = pose_emb;
+        const long long per_img = static_cast<long long>(h) * w * C0;
+        op([=](cudaStream_t s) { return broadcast_neg_images_run(small, per_img, F, full, s); });
+        release(small);
+        pose_emb = full;
+      }
     }
     Act x;
     {
@@ -961,7 +977,7 @@ Plan* Model::find_plan(int n_domains, int B, int F, int h, int w) {
   return nullptr;
 }
 
-int Model::get_plan(const int* domain_ids, int n_domains, int B, int F, int h, int w, Plan** out, int F_total) {
+int Model::get_plan(const int* domain_ids, int n_domains, int B, int F, int h, int w, Plan** out, int F_total, bool pose_shared_neg) {
   if (!finalized_) {
     set_error("weights not finalized (call d4d_finalize_weights)");
     return 3;
@@ -979,7 +995,7 @@ int Model::get_plan(const int* domain_ids, int n_domains, int B, int F, int h, i
     D4D_REQUIRE(xch_.ready && xch_.world > 1, "frame-sharded forward needs d4d_exchange_open first");
     D4D_REQUIRE(F * xch_.world == F_total, "F_total must equal world * local frames");
   }
-  const std::string key = plan_key(domain_ids, n_domains, B, F, h, w) + (sharded ? "_sh" + std::to_string(F_total) : std::string());
+  const std::string key = plan_key(domain_ids, n_domains, B, F, h, w) + (sharded ? "_sh" + std::to_string(F_total) : std::string()) + (pose_shared_neg ? "_pn" : "");
   auto it = plans_.find(key);
   if (it != plans_.end()) {
     *out = it->second.get();
@@ -990,12 +1006,14 @@ int Model::get_plan(const int* domain_ids, int n_domains, int B, int F, int h, i
   p->n_domains = n_domains; p->B = B; p->F = F; p->h = h; p->w = w;
   p->domains.assign(domain_ids, domain_ids + n_domains);
   if (sharded) { p->F_total = F_total; p->rank = xch_.rank; p->world = xch_.world; }
+  p->pose_shared_neg = pose_shared_neg && cfg_.enable_pose_encoder && n_domains == 2;
   size_t peak = 0;
   {
     Plan scratch;
     scratch.n_domains = n_domains; scratch.B = B; scratch.F = F; scratch.h = h; scratch.w = w;
     scratch.domains = p->domains;
     scratch.F_total = p->F_total; scratch.rank = p->rank; scratch.world = p->world;
+    scratch.pose_shared_neg = p->pose_shared_neg;
     PlanBuilder dry(*this, scratch, true, nullptr);
     if (int rc = dry.build()) return rc;
     peak = dry.peak();
@@ -1010,12 +1028,12 @@ int Model::get_plan(const int* domain_ids, int n_domains, int B, int F, int h, i
 }
 
 int Model::forward(const bf16* sample, const long long* timestep, const bf16* skeletons, const int* domain_ids,
-                   int n_domains, int B, int F, int h, int w, bf16* out, cudaStream_t stream, int F_total) {
+                   int n_domains, int B, int F, int h, int w, bf16* out, cudaStream_t stream, int F_total, bool pose_shared_neg) {
   D4D_REQUIRE(sample && timestep && out && domain_ids, "null argument");
   D4D_REQUIRE(!cfg_.enable_pose_encoder || skeletons != nullptr, "skeletons are required when enable_pose_encoder");
   D4D_REQUIRE(!cfg_.center_input_sample, "center_input_sample is not supported");
   Plan* p = nullptr;
-  if (int rc = get_plan(domain_ids, n_domains, B, F, h, w, &p, F_total)) return rc;
+  if (int rc = get_plan(domain_ids, n_domains, B, F, h, w, &p, F_total, pose_shared_neg)) return rc;
   D4D_CUDA_OK(cudaSetDevice(device_));
   p->sample = sample;
   p->timestep = timestep;
@@ -1133,7 +1151,10 @@ int Model::denoise_window(bf16* latents, const bf16* pixel, const bf16* plucker,
     const size_t hw = static_cast<size_t>(h) * w;
     D4D_CUDA_OK(cudaMalloc(&wb->sample, sizeof(bf16) * B * Cin * hw));
     D4D_CUDA_OK(cudaMalloc(&wb->timestep, sizeof(long long) * B));
-    if (pose) D4D_CUDA_OK(cudaMalloc(&wb->skel, sizeof(bf16) * B * 3 * 64 * hw));
+    if (pose) {
+      D4D_CUDA_OK(cudaMalloc(&wb->skel, sizeof(bf16) * (F + 1) * 3 * 64 * hw));
+      if (int rc = fill_bf16_run(wb->skel, static_cast<long long>(3) * 64 * hw, -1.0f, stream)) return rc;  // constant negative image
+    }
     D4D_CUDA_OK(cudaMalloc(&wb->noise, sizeof(bf16) * B * cfg_.out_channels * hw));
     D4D_CUDA_OK(cudaMalloc(&wb->latents_tmp, sizeof(bf16) * F * 4 * hw));
     D4D_CUDA_OK(cudaMalloc(&wb->ts_tmp, sizeof(long long) * F));
@@ -1151,14 +1172,15 @@ int Model::denoise_window(bf16* latents, const bf16* pixel, const bf16* plucker,
     if (int rc = assemble_input_run(a, stream)) return rc;
     const bf16* skel_in = nullptr;
     if (pose) {
-      if (cfg_on) {
-        if (int rc = cfg_skeleton_run(skeletons, static_cast<long long>(3) * 64 * hw, F, wb.skel, stream)) return rc;
+      if (cfg_on) {  // [negative (filled once) | F positive images]
+        D4D_CUDA_OK(cudaMemcpyAsync(wb.skel + static_cast<size_t>(3) * 64 * hw, skeletons, sizeof(bf16) * F * 3 * 64 * hw,
+                                    cudaMemcpyDeviceToDevice, stream));
         skel_in = wb.skel;
       } else {
         skel_in = skeletons;
       }
     }
-    if (int rc = forward(wb.sample, wb.timestep, skel_in, doms, cfg_on ? 2 : 1, B, F, h, w, wb.noise, stream, F_total)) return rc;
+    if (int rc = forward(wb.sample, wb.timestep, skel_in, doms, cfg_on ? 2 : 1, B, F, h, w, wb.noise, stream, F_total, pose && cfg_on)) return rc;
     DdimArgs d;
     d.noise = wb.noise; d.latents = latents; d.mask = mask; d.timestep_indices = ts_idx;
     d.timesteps_table = reinterpret_cast<const long long*>(sched.timesteps_table); d.alphas_cumprod = sched.alphas_cumprod;

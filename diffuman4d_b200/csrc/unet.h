@@ -47,6 +47,7 @@ struct Plan {
   int launches = 0;
   // frame-sharded window: this rank owns F of F_total frames per CFG half
   int F_total = 0, rank = 0, world = 1;
+  bool pose_shared_neg = false;  // skeleton batch = [1 CFG-negative image | F positive images] (window step)
   int n3d = 0;                 // number of 3-D attention layers (K/V exchanges) per forward
   unsigned int run_index = 0;  // forwards executed on this plan
   unsigned int epoch0 = 0;     // exchange counter at the start of the current forward (epoch / buffer parity per layer)
@@ -91,7 +92,8 @@ class Model {
   int finalize();
   // F_total > F: frame-sharded window (needs exchange_open); B, F are the LOCAL batch / frames
   int forward(const bf16* sample, const long long* timestep, const bf16* skeletons, const int* domain_ids,
-              int n_domains, int B, int F, int h, int w, bf16* out, cudaStream_t stream, int F_total = 0);
+              int n_domains, int B, int F, int h, int w, bf16* out, cudaStream_t stream, int F_total = 0,
+              bool pose_shared_neg = false);
   int exchange_alloc(size_t kv_bytes, unsigned char* handles_out /* 3 x 64 bytes */);
   int exchange_open(int rank, int world, const unsigned char* all_handles /* world x 3 x 64 bytes */);
   int denoise_window(bf16* latents, const bf16* pixel, const bf16* plucker, const bf16* skeletons, const bf16* mask,
@@ -101,7 +103,8 @@ class Model {
   int profile(const bf16* sample, const long long* timestep, const bf16* skeletons, const int* domain_ids, int n_domains,
               int B, int F, int h, int w, bf16* out, cudaStream_t stream, float* ms_by_kind, int* launches_by_kind,
               double* flops_by_kind);
-  int get_plan(const int* domain_ids, int n_domains, int B, int F, int h, int w, Plan** out, int F_total = 0);
+  int get_plan(const int* domain_ids, int n_domains, int B, int F, int h, int w, Plan** out, int F_total = 0,
+               bool pose_shared_neg = false);
   Plan* find_plan(int n_domains, int B, int F, int h, int w);
   const std::vector<std::string>& keys() const { return key_order_; }
   int device() const { return device_; }

@@ -141,6 +141,10 @@ int d4d_op_layernorm(const void* x, int rows, int C, float eps, const float* gam
 int d4d_op_probe_umma(const void* A, const void* B, float* D, int N, int K, int a_src, int b_major, uint32_t b_lbo,
                       uint32_t b_sbo, uint32_t b_kadv, void* stream);
 
+/* Device microbenchmarks that size the attention kernel: kind 0 tcgen05.ld x32, 1 tcgen05.ld x16, 2 tcgen05.st x16,
+ * 3 ex2.approx (8 per iteration), 4 cvt.bf16x2 (4 per iteration); `warps` per CTA, `blocks` CTAs; cycles_dev[blocks]. */
+int d4d_microbench(int kind, int warps, int iters, int blocks, uint64_t* cycles_dev, float* sink_dev, void* stream);
+
 /* ---- multi-GPU: frame-sharded window with fused K/V exchange over peer memory ------------
  * One process per GPU.  Rank r of `world` owns frames [r*F_local, (r+1)*F_local) of each CFG half (F_total = world *
  * F_local); everything except the 3-D attention is per image.  At each 3-D block the fused-QKV GEMM epilogue stores
