@@ -157,7 +157,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   uint64_t* pv_done = q_full + 7;  // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_full + 9);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // role branches are warp-uniform
   const int lane = threadIdx.x & 31;
   const int q_tile = blockIdx.x;
   const int bh = blockIdx.y;
@@ -186,11 +186,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  pdl_wait();
+  pdl_launch_dependents();
 
+  // Producer and MMA issuer run with the whole warp in uniform control flow and elect one lane around the asynchronous
+  // instructions only (single UTMALDG / UTCHMMA / UTCBAR instructions with uniform-register operands; see gemm_umma.cu).
   if (warp == 4) {
     // ============================ TMA producer ============================
-    if (lane == 0) {
+    if (elect_one()) {
       tma_prefetch_desc(&tmap_q);
       tma_prefetch_desc(&tmap_k);
       tma_prefetch_desc(&tmap_v);
@@ -198,35 +202,42 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 #pragma unroll
       for (int nb = 0; nb < NB; ++nb)
         tma_load_2d(sQ + nb * QTILE_BYTES, &tmap_q, q_full, col0 + nb * 64, q_row0 + q_tile * BLOCK_Q);
-      int slot = 0;
-      uint32_t phase = 0;
-      auto load_tile = [&](bool is_v, int j) {
-        mbar_wait(&ring_empty[slot], phase ^ 1);
-        uint8_t* dst = sRing + slot * C::SLOT_BYTES;
+    }
+    __syncwarp();
+    int slot = 0;
+    uint32_t phase = 0;
+    auto load_tile = [&](bool is_v, int j) {
+      mbar_wait(&ring_empty[slot], phase ^ 1);
+      uint8_t* dst = sRing + slot * C::SLOT_BYTES;
+      if (elect_one()) {
         if (a.dbg & 16) {  // ablation: no K/V traffic
           mbar_arrive(&ring_full[slot]);
         } else {
           mbar_expect_tx(&ring_full[slot], C::SLOT_BYTES);
 #pragma unroll
-          for (int nb = 0; nb < NB; ++nb)
-            tma_load_2d(dst + nb * KTILE_BYTES, is_v ? &tmap_v : &tmap_k, &ring_full[slot], col0 + nb * 64,
-                        kv_row0 + j * BLOCK_KV);
+          for (int nb = 0; nb < NB; ++nb) {
+            if (is_v) tma_load_2d(dst + nb * KTILE_BYTES, &tmap_v, &ring_full[slot], col0 + nb * 64, kv_row0 + j * BLOCK_KV);
+            else tma_load_2d(dst + nb * KTILE_BYTES, &tmap_k, &ring_full[slot], col0 + nb * 64, kv_row0 + j * BLOCK_KV);
+          }
         }
-        if (++slot == C::SLOTS) { slot = 0; phase ^= 1; }
-      };
-      // same order as the MMA warp consumes: K0 K1, then for every j: V(j), K(j+2)
-      load_tile(false, 0);
-      if (n_tiles > 1) load_tile(false, 1);
-      for (int j = 0; j < n_tiles; ++j) {
-        load_tile(true, j);
-        if (j + 2 < n_tiles) load_tile(false, j + 2);
       }
+      __syncwarp();
+      if (++slot == C::SLOTS) { slot = 0; phase ^= 1; }
+    };
+    // same order as the MMA warp consumes: K0 K1, then for every j: V(j), K(j+2)
+    load_tile(false, 0);
+    if (n_tiles > 1) load_tile(false, 1);
+    for (int j = 0; j < n_tiles; ++j) {
+      load_tile(true, j);
+      if (j + 2 < n_tiles) load_tile(false, j + 2);
     }
   } else if (warp == 5) {
-    // ============================ MMA issuer (lane 0 issues, the whole warp takes part in the named barriers) ============
+    // ============================ MMA issuer ============================
     const uint32_t idesc_qk = make_idesc_bf16(BLOCK_Q, BLOCK_KV, 0, 0);
     const uint32_t idesc_pv = make_idesc_bf16(BLOCK_Q, C::D, 0, 1);
     const uint32_t o_tmem = tmem + C::COL_O;
+    const uint32_t q_addr = smem_u32(sQ);
+    const uint32_t ring_addr = smem_u32(sRing);
     int slot = 0;
     uint32_t phase = 0;
     auto wait_ahead = [&](int k) {  // wait for the k-th next ring slot without consuming it
@@ -235,21 +246,21 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       if (sl >= C::SLOTS) { sl -= C::SLOTS; ph ^= 1; }
       mbar_wait(&ring_full[sl], ph);
     };
-    auto issue_qk = [&](int j) {  // S[j&1] = Q K_j^T   (operands already waited for)
-      const uint32_t kaddr = smem_u32(sRing + slot * C::SLOT_BYTES);
+    auto issue_qk = [&](int j, int sl) {  // S[j&1] = Q K_j^T   (operands already waited for; elected lane only)
+      const uint32_t kaddr = ring_addr + sl * C::SLOT_BYTES;
       const uint32_t s_tmem = tmem + C::COL_S + (j & 1) * 64;
 #pragma unroll
       for (int nb = 0; nb < NB; ++nb) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const uint64_t ad = make_smem_desc(smem_u32(sQ) + nb * QTILE_BYTES + k * 32, 0, 1024, 2);
+          const uint64_t ad = make_smem_desc(q_addr + nb * QTILE_BYTES + k * 32, 0, 1024, 2);
           const uint64_t bd = make_smem_desc(kaddr + nb * KTILE_BYTES + k * 32, 0, 1024, 2);
           if (!(a.dbg & 8)) umma_ss(s_tmem, ad, bd, idesc_qk, (nb | k) != 0 ? 1u : 0u);
         }
       }
     };
-    auto issue_pv = [&](int j) {  // O += P[j&1] V_j     (operands already waited for)
-      const uint32_t vaddr = smem_u32(sRing + slot * C::SLOT_BYTES);
+    auto issue_pv = [&](int j, int sl) {  // O += P[j&1] V_j     (operands already waited for; elected lane only)
+      const uint32_t vaddr = ring_addr + sl * C::SLOT_BYTES;
       const uint32_t p_tmem = tmem + C::COL_P + (j & 1) * 32;
 #pragma unroll
       for (int k = 0; k < BLOCK_KV / 16; ++k) {
@@ -264,52 +275,43 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       if (++slot == C::SLOTS) { slot = 0; phase ^= 1; }
       return used;
     };
-    if (lane == 0) {
-      mbar_wait(q_full, 0);
+    mbar_wait(q_full, 0);
+    for (int j0 = 0; j0 < 2 && j0 < n_tiles; ++j0) {  // prologue: S(0), S(1)
       wait_ahead(0);
-      tc_fence_after();
-      issue_qk(0);
-      umma_commit(&s_full[0]);
-      umma_commit(&ring_empty[advance()]);
-      if (n_tiles > 1) {
-        wait_ahead(0);
-        tc_fence_after();
-        issue_qk(1);
-        umma_commit(&s_full[1]);
-        umma_commit(&ring_empty[advance()]);
-      }
-    }
-    slot = __shfl_sync(0xffffffffu, slot, 0);
-    phase = __shfl_sync(0xffffffffu, phase, 0);
-    for (int j = 0; j < n_tiles; ++j) {
-      if (lane == 0) {  // operands of this iteration, waited for BEFORE the critical-path barrier
-        wait_ahead(0);                      // V(j)
-        if (j + 2 < n_tiles) wait_ahead(1);  // K(j+2)
+      const int k_slot = advance();
+      if (elect_one()) {
+        issue_qk(j0, k_slot);
+        umma_commit(&s_full[j0]);
+        umma_commit(&ring_empty[k_slot]);
       }
       __syncwarp();
+    }
+    for (int j = 0; j < n_tiles; ++j) {
+      // operands of this iteration, waited for BEFORE the critical-path barrier
+      const bool more = j + 2 < n_tiles;
+      wait_ahead(0);            // V(j)
+      if (more) wait_ahead(1);  // K(j+2)
+      const int v_slot = advance();
+      const int k_slot = more ? advance() : 0;
       // P(j) ready also means S(j) has been consumed.  P.V(j) is issued BEFORE Q.K(j+2): tcgen05.commit covers all
       // earlier MMAs of this thread, so s_full(j+2) doubles as "P.V(j) done" and the softmax warps need no separate
       // wait before reusing the P buffer two tiles later.
       pready_sync(j & 1);
-      if (lane == 0) {
-        tc_fence_after();
-        issue_pv(j);
-        const int v_slot = advance();
-        if (j + 2 < n_tiles) {
-          issue_qk(j + 2);
-          // the commit the softmax warps are waiting for goes FIRST (each tcgen05.commit takes a few hundred cycles to
-          // issue and they serialise); it covers P.V(j) as well as Q.K(j+2)
-          umma_commit(&s_full[j & 1]);
+      tc_fence_after();  // P was written with tcgen05.st by the softmax warps
+      if (elect_one()) {
+        issue_pv(j, v_slot);
+        if (more) {
+          issue_qk(j + 2, k_slot);
+          umma_commit(&s_full[j & 1]);  // the commit the softmax warps wait for goes first; it covers P.V(j) too
           umma_commit(&pv_done[j & 1]);
           umma_commit(&ring_empty[v_slot]);
-          umma_commit(&ring_empty[advance()]);
+          umma_commit(&ring_empty[k_slot]);
         } else {
           umma_commit(&pv_done[j & 1]);
           umma_commit(&ring_empty[v_slot]);
         }
       }
-      slot = __shfl_sync(0xffffffffu, slot, 0);
-      phase = __shfl_sync(0xffffffffu, phase, 0);
+      __syncwarp();
     }
   } else {
     // ============================ softmax / correction / epilogue ============================
@@ -349,6 +351,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       const uint32_t par = (j >> 1) & 1;
       const uint32_t p_tmem = tmem + C::COL_P + buf * 32 + lane_sel;
       tmem_ld_wait();  // S(j) is in registers
+      // Q.K runs two tiles ahead, so S(j+1) is normally complete by now: probe it here (non-blocking) and skip the
+      // ~200-cycle try_wait at the end of the iteration when the probe succeeded
+      const bool next_ready = (j + 1 < n_tiles) && __all_sync(0xffffffffu, mbar_test(&s_full[buf ^ 1], ((j + 1) >> 1) & 1));
 
       float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
       if (a.dbg & 64) {  // ablation: barriers only
@@ -412,7 +417,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       tc_fence_before();
       pready_arrive(buf);  // hand P(j) to the MMA warp FIRST: the wait below must not delay P.V(j) / Q.K(j+2)
       if (j + 1 < n_tiles) {  // then fetch S(j+1) (Q.K runs two tiles ahead); its latency overlaps the hand-off
-        mbar_wait(&s_full[buf ^ 1], ((j + 1) >> 1) & 1);
+        if (!next_ready) mbar_wait(&s_full[buf ^ 1], ((j + 1) >> 1) & 1);
         tc_fence_after();
         const uint32_t s_next = tmem + C::COL_S + (buf ^ 1) * 64 + lane_sel;
         if (!(a.dbg & 32)) {
@@ -479,7 +484,7 @@ int launch_attn(const AttnLaunch& L, cudaStream_t stream) {
     a.dbg = dbg;
   }
   dim3 grid(L.grid_x, L.grid_y);
-  attn_fwd_kernel<NB><<<grid, ATT_THREADS, C::SMEM_BYTES, stream>>>(L.tmap_q, L.tmap_k, L.tmap_v, a);
+  D4D_CUDA_OK(launch_pdl(attn_fwd_kernel<NB>, grid, dim3(ATT_THREADS), C::SMEM_BYTES, stream, L.tmap_q, L.tmap_k, L.tmap_v, a));
   D4D_CUDA_OK(cudaGetLastError());
   return 0;
 }

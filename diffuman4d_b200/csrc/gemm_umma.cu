@@ -27,15 +27,22 @@ namespace {
 
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;
-constexpr int STAGES = 4;
+constexpr int MAX_STAGES = 8;
 constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;     // 16 KB
-constexpr int B_BYTES_MAX = 256 * BLOCK_K * 2;     // 32 KB
-constexpr int STAGE_BYTES = A_BYTES + B_BYTES_MAX; // 48 KB
+constexpr int BAR_BYTES = 1024;                    // barrier block in front of the ring keeps the stages 1024-B aligned
+constexpr int SMEM_BYTES = 227 * 1024;             // everything an SM has: the ring gets as many stages as fit
+constexpr int RING_BYTES = SMEM_BYTES - 1024 /*align*/ - BAR_BYTES;
+// The main loop is bound by the latency of the TMA loads in flight (measured: ~650-700 cycles per k-block whatever block_n
+// is, with 4 x 48 KB stages), so the ring depth follows the tile width: 4 stages at block_n 256 ... 8 at block_n <= 96.
+__host__ __device__ inline int stage_bytes_for(int block_n) { return A_BYTES + block_n * BLOCK_K * 2; }
+__host__ __device__ inline int stages_for(int block_n) {
+  const int s = RING_BYTES / stage_bytes_for(block_n);
+  return s > MAX_STAGES ? MAX_STAGES : s;
+}
 constexpr int EPI_WARPS_PER_QUARTER = 3;
 constexpr int NUM_THREADS = 64 + 128 * EPI_WARPS_PER_QUARTER;  // warp0 TMA, warp1 MMA(+TMEM alloc), then the epilogue warps
 constexpr int TMEM_COLS = 512;
 constexpr int ACC_STRIDE = 256;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 
 struct TileCoord {
   int m0;          // plain: first row.  conv: unused
@@ -73,14 +80,17 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for the 128B swizzle atoms
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
-  uint64_t* full = bars;               // [STAGES]
-  uint64_t* empty = bars + STAGES;     // [STAGES]
-  uint64_t* tfull = bars + 2 * STAGES; // [2]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+  smem += BAR_BYTES;
+  uint64_t* full = bars;                   // [MAX_STAGES]
+  uint64_t* empty = bars + MAX_STAGES;     // [MAX_STAGES]
+  uint64_t* tfull = bars + 2 * MAX_STAGES; // [2]
+  const int STAGES = stages_for(a.block_n);
+  const int STAGE_BYTES = stage_bytes_for(a.block_n);
   uint64_t* tempty = tfull + 2;        // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // tells the compiler the role branches are warp-uniform
   const int lane = threadIdx.x & 31;
   const int total_tiles = a.m_tiles * a.n_tiles;
   const uint32_t b_bytes = static_cast<uint32_t>(a.block_n) * BLOCK_K * 2;
@@ -103,69 +113,93 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  pdl_wait();  // barriers / TMEM are set up while the previous kernel drains
+  pdl_launch_dependents();
 
+  // The producer and the MMA issuer run their loops with the WHOLE warp in uniform control flow and elect one lane only
+  // around the asynchronous instructions: descriptors / coordinates then live in uniform registers and every
+  // UTMALDG / UTCHMMA is a single instruction.  (With the loop inside `if (lane == 0)` the compiler wraps each of them
+  // in an ELECT + 5x R2UR + branch sequence, and the issuing thread - not the tensor pipe - bounds the main loop:
+  // measured ~650-800 cycles per k-block for every block_n, profiles/README.md.)
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m_tile = tile / a.n_tiles;
-        const int n_tile = tile % a.n_tiles;
-        TileCoord tc;
-        tile_coords(a, m_tile, tc);
-        const int n0 = n_tile * a.block_n;
-        for (int kb = 0; kb < a.k_blocks; ++kb) {
-          mbar_wait(&empty[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * STAGE_BYTES;
-          uint8_t* sb = sa + A_BYTES;
-          mbar_expect_tx(&full[stage], A_BYTES + b_bytes);
-          if (a.mode == 0) {
-            if (kb < a.kb_split) tma_load_2d(sa, &tmap_a, &full[stage], kb * BLOCK_K, tc.m0);
-            else tma_load_2d(sa, &tmap_a2, &full[stage], (kb - a.kb_split) * BLOCK_K, tc.m0);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int m_tile = tile / a.n_tiles;
+      const int n_tile = tile % a.n_tiles;
+      TileCoord tc;
+      tile_coords(a, m_tile, tc);
+      const int n0 = n_tile * a.block_n;
+      for (int kb = 0; kb < a.k_blocks; ++kb) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * STAGE_BYTES;
+        uint8_t* sb = sa + A_BYTES;
+        if (a.dbg & 1) {  // ablation: no loads (D4D_GEMM_ABLATE)
+          if (elect_one()) mbar_arrive(&full[stage]);
+        } else if (a.mode == 0) {
+          const bool first = kb < a.kb_split;
+          const int ka = first ? kb * BLOCK_K : (kb - a.kb_split) * BLOCK_K;
+          if (elect_one()) {
+            mbar_expect_tx(&full[stage], A_BYTES + b_bytes);
+            if (first) tma_load_2d(sa, &tmap_a, &full[stage], ka, tc.m0);
+            else tma_load_2d(sa, &tmap_a2, &full[stage], ka, tc.m0);
             tma_load_2d(sb, &tmap_b, &full[stage], kb * BLOCK_K, n0);
-          } else {
-            const int tap = kb / a.cin_blocks;
-            const int cb = kb - tap * a.cin_blocks;
-            const int ky = tap / 3, kx = tap - ky * 3;
+          }
+        } else {
+          const int tap = kb / a.cin_blocks;
+          const int cb = kb - tap * a.cin_blocks;
+          const int ky = tap / 3, kx = tap - ky * 3;
+          if (elect_one()) {
+            mbar_expect_tx(&full[stage], A_BYTES + b_bytes);
             tma_load_4d(sa, &tmap_a, &full[stage], cb * BLOCK_K, tc.x0 + kx - 1, tc.y0 + ky - 1, tc.n_img0);
             tma_load_2d(sb, &tmap_b, &full[stage], tap * a.Cin + cb * BLOCK_K, n0);
           }
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     const uint32_t idesc = make_idesc_bf16(BLOCK_M, a.block_n, 0, 0);
+    const uint32_t ring = smem_u32(smem);
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
+    bool ready = false;  // full[stage] already seen complete by the probe of the previous k-block
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      if (lane == 0) {
-        mbar_wait(&tempty[acc], acc_phase ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * ACC_STRIDE;
-        for (int kb = 0; kb < a.k_blocks; ++kb) {
-          mbar_wait(&full[stage], phase);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-          const uint32_t sb = sa + A_BYTES;
-          const uint64_t adesc = make_smem_desc(sa, 0, 1024, 2);
-          const uint64_t bdesc = make_smem_desc(sb, 0, 1024, 2);
+      mbar_wait(&tempty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * ACC_STRIDE;
+      for (int kb = 0; kb < a.k_blocks; ++kb) {
+        // operands were written by TMA: the mbarrier orders them, no tcgen05 fence needed
+        if (!ready) mbar_wait(&full[stage], phase);
+        const uint32_t sa = ring + stage * STAGE_BYTES;
+        const uint64_t adesc = make_smem_desc(sa, 0, 1024, 2);
+        const uint64_t bdesc = make_smem_desc(sa + A_BYTES, 0, 1024, 2);
+        {  // probe the next stage now; the answer is needed only after this k-block's MMAs have been issued
+          const int ns = stage + 1 == STAGES ? 0 : stage + 1;
+          const uint32_t np = stage + 1 == STAGES ? phase ^ 1 : phase;
+          ready = __all_sync(0xffffffffu, mbar_test(&full[ns], np));
+        }
+        if (elect_one()) {
+          if (!(a.dbg & 2)) {
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / 16; ++k) {
-            // advancing 16 bf16 along K inside the 128B swizzle atom = +32 bytes = +2 in the (addr>>4) field
-            umma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BLOCK_K / 16; ++k) {
+              // advancing 16 bf16 along K inside the 128B swizzle atom = +32 bytes = +2 in the (addr>>4) field
+              umma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
           }
           umma_commit(&empty[stage]);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull[acc]);
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
+      if (elect_one()) umma_commit(&tfull[acc]);
       __syncwarp();
     }
   } else {
@@ -379,6 +413,14 @@ int gemm_prepare(const GemmDesc& d, GemmLaunch* L) {
   }
   D4D_REQUIRE(bn >= 16 && d.N % bn == 0 && bn % (d.geglu ? 32 : 16) == 0, "no valid block_n");
   a.block_n = bn;
+  {
+    static int dbg = -1;
+    if (dbg < 0) {
+      const char* e = getenv("D4D_GEMM_ABLATE");
+      dbg = e ? atoi(e) : 0;
+    }
+    a.dbg = dbg;
+  }
   a.n_tiles = d.N / bn;
   a.N = d.N;
   a.bias = d.bias;
@@ -455,10 +497,10 @@ int gemm_run(const GemmLaunch& L, cudaStream_t stream) {
   static bool attr_set[2][64] = {};
   if (L.args.geglu) {
     if (int rc = ensure_dyn_smem(gemm_umma_kernel<true>, SMEM_BYTES, attr_set[1])) return rc;
-    gemm_umma_kernel<true><<<L.grid, NUM_THREADS, SMEM_BYTES, stream>>>(L.tmap_a, L.tmap_a2, L.tmap_b, L.args);
+    D4D_CUDA_OK(launch_pdl(gemm_umma_kernel<true>, dim3(L.grid), dim3(NUM_THREADS), SMEM_BYTES, stream, L.tmap_a, L.tmap_a2, L.tmap_b, L.args));
   } else {
     if (int rc = ensure_dyn_smem(gemm_umma_kernel<false>, SMEM_BYTES, attr_set[0])) return rc;
-    gemm_umma_kernel<false><<<L.grid, NUM_THREADS, SMEM_BYTES, stream>>>(L.tmap_a, L.tmap_a2, L.tmap_b, L.args);
+    D4D_CUDA_OK(launch_pdl(gemm_umma_kernel<false>, dim3(L.grid), dim3(NUM_THREADS), SMEM_BYTES, stream, L.tmap_a, L.tmap_a2, L.tmap_b, L.args));
   }
   D4D_CUDA_OK(cudaGetLastError());
   return 0;

@@ -1,6 +1,8 @@
 // Internal kernel-launcher interface shared by the op-level C-ABI (d4d_api.cu) and the UNet
 // executor (unet.cu).  Every launcher returns 0 on success, non-zero after d4d::set_error().
 #pragma once
+#include <cstdlib>
+#include <utility>
 #include <string.h>
 
 #include "common.cuh"
@@ -11,6 +13,7 @@ namespace d4d {
 // tcgen05 GEMM / implicit-GEMM conv3x3  (gemm_umma.cu)
 // --------------------------------------------------------------------------------------------
 struct GemmKernelArgs {
+  int dbg;  // ablation switches (tools/ablate_gemm.py); 0 in production
   int M, N, k_blocks, block_n, n_tiles, m_tiles;
   int mode;      // 0 plain, 1 conv3x3 (stride 1, pad 1, NHWC)
   int kb_split;  // plain: k-blocks served by A (rest by A2)
@@ -204,6 +207,32 @@ inline int ensure_dyn_smem(F func, int bytes, bool* done_per_device) {
     done_per_device[dev] = true;
   }
   return 0;
+}
+
+// Programmatic dependent launch: the kernel may become resident while its predecessor in the stream drains; it must
+// execute pdl_wait() (common.cuh) before touching anything a predecessor wrote.  Measured on the W16 step: 46.63 ms with the
+// attribute vs 46.55 ms without (the kernels are long enough that launch gaps do not show), so it is opt-in: D4D_PDL=1.
+inline bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("D4D_PDL");
+    on = (e && e[0] == '1') ? 1 : 0;
+  }
+  return on == 1;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
 }  // namespace d4d

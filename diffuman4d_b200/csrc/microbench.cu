@@ -8,6 +8,9 @@ namespace {
 // kind 0: tcgen05.ld 32x32b.x32   1: tcgen05.ld 32x32b.x16   2: tcgen05.st 32x32b.x16   3: ex2.approx   4: cvt.bf16x2
 __global__ void microbench_kernel(int kind, int iters, unsigned long long* cycles, float* sink) {
   __shared__ uint32_t slot;
+  __shared__ uint64_t bars[9];
+  __shared__ __align__(1024) uint8_t tile[2][128 * 128];
+  uint64_t& bar = bars[0];
   const int warp = threadIdx.x >> 5;
   if (warp == 0) tmem_alloc(&slot, 512);
   tc_fence_before();
@@ -50,8 +53,6 @@ __global__ void microbench_kernel(int kind, int iters, unsigned long long* cycle
     }
   } else if (kind == 7 || kind == 8) {
     // latency of tcgen05.commit -> mbarrier completion -> try_wait return (kind 8: preceded by one 128x64x16 MMA)
-    __shared__ uint64_t bar;
-    __shared__ __align__(1024) uint8_t tile[2][128 * 128];
     if (threadIdx.x == 0) {
       mbar_init(&bar, 1);
       fence_mbar_init();
@@ -67,6 +68,58 @@ __global__ void microbench_kernel(int kind, int iters, unsigned long long* cycle
         mbar_wait(&bar, ph);
         ph ^= 1;
       }
+    }
+  } else if (kind >= 9 && kind <= 16) {
+    // tensor-pipe throughput of back-to-back 128xNx16 MMAs with / without interleaved tcgen05.commit (nobody waits on the
+    // barriers except for the last one):
+    //   9: N=256, no commits   10: N=256, commit every 4 MMAs   11: N=64, no commits   12: N=64, commit every 4 MMAs
+    //  13: commits only        14: N=256, commit every 16 MMAs  15: N=160, no commits  16: N=160, commit every 4 MMAs
+    if (threadIdx.x == 0) {
+      for (int i = 0; i < 9; ++i) mbar_init(&bars[i], 1);
+      fence_mbar_init();
+      const int N = (kind == 11 || kind == 12) ? 64 : (kind >= 15 ? 160 : 256);
+      const int every = (kind == 10 || kind == 12 || kind == 16) ? 4 : (kind == 14 ? 16 : (kind == 13 ? 1 : 0));
+      const uint32_t idesc = make_idesc_bf16(128, N, 0, 0);
+      const uint64_t ad = make_smem_desc(smem_u32(tile[0]), 0, 1024, 2);
+      const uint64_t bd = make_smem_desc(smem_u32(tile[0]), 0, 1024, 2);
+      int b = 0;
+      for (int i = 0; i < iters; ++i) {
+        if (kind != 13) umma_ss(tmem + (i & 1) * 256, ad + 2 * (i & 3), bd + 2 * (i & 3), idesc, 1);
+        if (every && (i % every) == every - 1) {
+          umma_commit(&bars[b]);
+          b = (b + 1) & 7;
+        }
+      }
+      umma_commit(&bars[8]);
+      mbar_wait(&bars[8], 0);
+    }
+  } else if (kind == 17 || kind == 18) {
+    // issue cost of tcgen05.fence::after_thread_sync (17) / of a try_wait on an already completed barrier phase (18)
+    if (threadIdx.x == 0) {
+      mbar_init(&bars[0], 1);
+      fence_mbar_init();
+      mbar_arrive(&bars[0]);  // phase 0 complete
+      for (int i = 0; i < iters; ++i) {
+        if (kind == 17) tc_fence_after();
+        else mbar_wait(&bars[0], 0);
+      }
+    }
+  } else if (kind >= 19 && kind <= 24) {
+    // 19: N=64 MMAs issued from two threads of different warps (is the 114-cycle floor the pipe or the issuing thread?)
+    // 20..24: one thread, no commits, N = 128 / 192 / 224 / 32 / 240
+    const int N = kind == 19 ? 64 : (kind == 20 ? 128 : (kind == 21 ? 192 : (kind == 22 ? 224 : (kind == 23 ? 32 : 240))));
+    const int issuers = kind == 19 ? 2 : 1;
+    if (threadIdx.x == 0) {
+      for (int i = 0; i < 9; ++i) mbar_init(&bars[i], 1);
+      fence_mbar_init();
+    }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0 && warp < issuers) {
+      const uint32_t idesc = make_idesc_bf16(128, N, 0, 0);
+      const uint64_t ad = make_smem_desc(smem_u32(tile[0]), 0, 1024, 2);
+      for (int i = 0; i < iters / issuers; ++i) umma_ss(tmem + warp * 256, ad + 2 * (i & 3), ad + 2 * (i & 3), idesc, 1);
+      umma_commit(&bars[warp]);
+      mbar_wait(&bars[warp], 0);
     }
   } else if (kind == 2) {
     uint32_t v[16];
@@ -118,7 +171,7 @@ __global__ void microbench_kernel(int kind, int iters, unsigned long long* cycle
 }  // namespace
 
 int microbench_run(int kind, int warps, int iters, int blocks, unsigned long long* cycles_dev, float* sink_dev, cudaStream_t s) {
-  D4D_REQUIRE(kind >= 0 && kind <= 8 && warps >= 1 && warps <= 16 && iters > 0 && blocks > 0, "microbench arguments");
+  D4D_REQUIRE(kind >= 0 && kind <= 24 && warps >= 1 && warps <= 16 && iters > 0 && blocks > 0, "microbench arguments");
   microbench_kernel<<<blocks, warps * 32, 0, s>>>(kind, iters, cycles_dev, sink_dev);
   D4D_CUDA_OK(cudaGetLastError());
   return 0;

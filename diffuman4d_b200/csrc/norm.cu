@@ -58,6 +58,8 @@ __global__ void __launch_bounds__(GN_MAX_THREADS, 2) gn_stats_kernel(const GnArg
   const int p1 = min(a.hw, p0 + a.pps);
   const int npix = p1 - p0;
   float* scratch = sm + 2 * a.C;  // [rows_per_iter][C][2]
+  pdl_wait();
+  pdl_launch_dependents();
 
   float s[8], ss[8], piv[8];
 #pragma unroll
@@ -177,6 +179,8 @@ __global__ void __launch_bounds__(GN_MAX_THREADS, 2) gn_stats_kernel(const GnArg
 __global__ void __launch_bounds__(GN_MAX_THREADS, 2) gn_apply_kernel(const GnArgs a) {
   extern __shared__ float sm[];
   const int split = blockIdx.x, img = blockIdx.y;
+  pdl_wait();
+  pdl_launch_dependents();
   for (int g = threadIdx.x; g < 2 * a.groups; g += blockDim.x)
     sm[(g & 1) * a.groups + (g >> 1)] = a.final_stats[static_cast<size_t>(img) * a.groups * 2 + g];
   __syncthreads();
@@ -227,6 +231,8 @@ __global__ void layernorm_kernel(const bf16* __restrict__ x, int rows, int C, fl
                                  const float* __restrict__ beta, bf16* __restrict__ out) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
+  pdl_wait();
+  pdl_launch_dependents();
   if (warp >= rows) return;
   const int n_oct = C / 8;
   const bf16* xr = x + static_cast<size_t>(warp) * C;
@@ -327,9 +333,9 @@ int groupnorm_run(const bf16* x1, int C1, const bf16* x2, int C2, int n_img, int
   dim3 grid(a.splits, n_img);
   const size_t smem_stats = sizeof(float) * (2 * C + 2 * static_cast<size_t>(a.rows_per_iter) * C);
   D4D_REQUIRE(smem_stats <= 48 * 1024, "GroupNorm stats smem");
-  gn_stats_kernel<<<grid, threads, smem_stats, stream>>>(a);
+  D4D_CUDA_OK(launch_pdl(gn_stats_kernel, grid, dim3(threads), smem_stats, stream, a));
   D4D_CUDA_OK(cudaGetLastError());
-  gn_apply_kernel<<<grid, threads, sizeof(float) * 2 * groups, stream>>>(a);
+  D4D_CUDA_OK(launch_pdl(gn_apply_kernel, grid, dim3(threads), sizeof(float) * 2 * groups, stream, a));
   D4D_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -342,10 +348,10 @@ int layernorm_run(const bf16* x, int rows, int C, float eps, const float* gamma,
   const int wpb = threads / 32;
   const int blocks = (rows + wpb - 1) / wpb;
   const int chunks = (C / 8 + 31) / 32;
-  if (chunks <= 2) layernorm_kernel<2><<<blocks, threads, 0, stream>>>(x, rows, C, eps, gamma, beta, out);
-  else if (chunks <= 4) layernorm_kernel<4><<<blocks, threads, 0, stream>>>(x, rows, C, eps, gamma, beta, out);
-  else if (chunks <= 5) layernorm_kernel<5><<<blocks, threads, 0, stream>>>(x, rows, C, eps, gamma, beta, out);
-  else layernorm_kernel<8><<<blocks, threads, 0, stream>>>(x, rows, C, eps, gamma, beta, out);
+  if (chunks <= 2) D4D_CUDA_OK(launch_pdl(layernorm_kernel<2>, dim3(blocks), dim3(threads), 0, stream, x, rows, C, eps, gamma, beta, out));
+  else if (chunks <= 4) D4D_CUDA_OK(launch_pdl(layernorm_kernel<4>, dim3(blocks), dim3(threads), 0, stream, x, rows, C, eps, gamma, beta, out));
+  else if (chunks <= 5) D4D_CUDA_OK(launch_pdl(layernorm_kernel<5>, dim3(blocks), dim3(threads), 0, stream, x, rows, C, eps, gamma, beta, out));
+  else D4D_CUDA_OK(launch_pdl(layernorm_kernel<8>, dim3(blocks), dim3(threads), 0, stream, x, rows, C, eps, gamma, beta, out));
   D4D_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -1,0 +1,10 @@
+#!/bin/bash
+# ops tests -> block_n sweep -> bench with and without programmatic dependent launch
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gpu_ops.py -m gpu -q -x > gpurun_out/test_ops.log 2>&1; echo "ops rc=$?"; tail -3 gpurun_out/test_ops.log
+timeout 500 python tools/tune_block_n.py > gpurun_out/tune_block_n.txt 2>&1; echo "tune rc=$?"
+for pdl in 0 1; do
+  D4D_PDL=$pdl timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_pdl$pdl.log 2>&1; echo "bench pdl=$pdl rc=$?"
+  tail -1 gpurun_out/bench_pdl$pdl.log | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['roofline']['by_kind_ms'], d['roofline']['by_kind_tflops'])"
+done
+timeout 900 python -m pytest tests/test_gpu_unet.py -m gpu -q -x > gpurun_out/test_unet.log 2>&1; echo "unet rc=$?"; tail -3 gpurun_out/test_unet.log

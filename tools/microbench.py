@@ -18,6 +18,28 @@ for kind in (7, 8):
         check(lib().d4d_microbench(kind, 4, iters, 148, cyc.data_ptr(), sink.data_ptr(), torch.cuda.current_stream().cuda_stream))
     torch.cuda.synchronize()
     print(f"tcgen05.commit -> mbarrier -> try_wait round trip ({'after one MMA' if kind == 8 else 'empty pipe'}): {cyc.float().mean().item() / iters:8.1f} cycles", flush=True)
+pipe = {9: ("N=256, no commits", 256), 10: ("N=256, commit / 4 MMAs", 256), 14: ("N=256, commit / 16 MMAs", 256),
+        15: ("N=160, no commits", 160), 16: ("N=160, commit / 4 MMAs", 160), 11: ("N=64, no commits", 64),
+        12: ("N=64, commit / 4 MMAs", 64), 13: ("commits only", 0)}
+for kind, (label, n) in pipe.items():
+    iters = 4096
+    for _ in range(2):
+        check(lib().d4d_microbench(kind, 4, iters, 148, cyc.data_ptr(), sink.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    c = cyc.float().mean().item() / iters
+    print(f"tensor pipe, 128xNx16 MMAs back to back, {label:26s}: {c:7.1f} cycles / MMA" + (f"  ({128 * n * 16 * 2 / c:7.0f} FLOP/clk/SM)" if n else ""), flush=True)
+extra = {20: ("N=128, no commits", 128), 21: ("N=192, no commits", 192), 22: ("N=224, no commits", 224), 24: ("N=240, no commits", 240),
+         23: ("N=32, no commits", 32), 19: ("N=64, issued by 2 threads", 64), 17: ("tcgen05.fence::after only", 0),
+         18: ("successful try_wait only", 0)}
+for kind, (label, n) in extra.items():
+    iters = 4096
+    for _ in range(2):
+        check(lib().d4d_microbench(kind, 4, iters, 148, cyc.data_ptr(), sink.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    c = cyc.float().mean().item() / iters
+    print(f"{label:34s}: {c:7.1f} cycles / iteration" + (f"  ({128 * n * 16 * 2 / c:7.0f} FLOP/clk/SM)" if n else ""), flush=True)
+if "--pipe-only" in sys.argv:
+    sys.exit(0)
 for kind in (0, 1, 5, 6, 2, 3, 4):
     for warps in (4, 8, 16):
         iters = 4000
