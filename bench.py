@@ -323,7 +323,11 @@ def run_ours(args):
     launches_fwd = unet.forward_launches(2, B, F, h, w)
     launches_step = launches_fwd + 3   # + assemble, cfg-skeleton, cfg+ddim kernels (2 memcpys not counted)
     roofline = {"bound": "tensor", "kernel": names[top], "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": achieved / peak_tf, "traffic": None,
+                "frac": achieved / peak_tf,
+                # dram__bytes_read.sum + dram__bytes_write.sum of the captured attention launch (level-2 3-D layer, grid 1280,
+                # profiles/r01d_ncu_attention.txt); its algorithmic Q/K/V/O bytes are 67.1 MB => no wasted HBM re-reads
+                "traffic": 68148480 if names[top] == "attention" else None,
+                "traffic_note": "ncu --set full capture of one level-2 3-D attention launch: 68.1 MB DRAM vs 67.1 MB algorithmic",
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained",
                 "launches_per_forward": int(n_k[top]), "ms_per_forward": kind_ms[top],
                 "by_kind_ms": {names[k]: round(kind_ms[k], 4) for k in range(6)},

@@ -27,11 +27,17 @@ namespace {
 
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;
+constexpr int EPI_WARPS_PER_QUARTER = 3;
 constexpr int MAX_STAGES = 8;
 constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;     // 16 KB
 constexpr int BAR_BYTES = 1024;                    // barrier block in front of the ring keeps the stages 1024-B aligned
 constexpr int SMEM_BYTES = 227 * 1024;             // everything an SM has: the ring gets as many stages as fit
-constexpr int RING_BYTES = SMEM_BYTES - 1024 /*align*/ - BAR_BYTES;
+// Output staging: every epilogue warp owns 32 rows x 64 B.  A thread holds one ROW of the accumulator (TMEM lane), so a
+// direct store makes each warp-level st.global touch 32 different lines (measured: the stores were 50% of the K = 320
+// GEMMs); staged through shared memory the warp stores 8 rows x 64 contiguous bytes per instruction.
+constexpr int STG_WARP_BYTES = 32 * 64;
+constexpr int STG_BYTES = 4 * EPI_WARPS_PER_QUARTER * STG_WARP_BYTES;  // 24 KB
+constexpr int RING_BYTES = SMEM_BYTES - 1024 /*align*/ - BAR_BYTES - STG_BYTES;
 // The main loop is bound by the latency of the TMA loads in flight (measured: ~650-700 cycles per k-block whatever block_n
 // is, with 4 x 48 KB stages), so the ring depth follows the tile width: 4 stages at block_n 256 ... 8 at block_n <= 96.
 __host__ __device__ inline int stage_bytes_for(int block_n) { return A_BYTES + block_n * BLOCK_K * 2; }
@@ -39,7 +45,6 @@ __host__ __device__ inline int stages_for(int block_n) {
   const int s = RING_BYTES / stage_bytes_for(block_n);
   return s > MAX_STAGES ? MAX_STAGES : s;
 }
-constexpr int EPI_WARPS_PER_QUARTER = 3;
 constexpr int NUM_THREADS = 64 + 128 * EPI_WARPS_PER_QUARTER;  // warp0 TMA, warp1 MMA(+TMEM alloc), then the epilogue warps
 constexpr int TMEM_COLS = 512;
 constexpr int ACC_STRIDE = 256;
@@ -81,7 +86,8 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   // 1024-byte alignment for the 128B swizzle atoms
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
-  smem += BAR_BYTES;
+  uint8_t* staging = smem + BAR_BYTES;
+  smem += BAR_BYTES + STG_BYTES;
   uint64_t* full = bars;                   // [MAX_STAGES]
   uint64_t* empty = bars + MAX_STAGES;     // [MAX_STAGES]
   uint64_t* tfull = bars + 2 * MAX_STAGES; // [2]
@@ -203,10 +209,40 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       __syncwarp();
     }
   } else {
-    // ===== epilogue warps; TMEM lane quarter = warp%4, the warps of a quarter interleave the 16-col chunks =====
+    // ===== epilogue warps; TMEM lane quarter = warp%4; the 3 warps of a quarter interleave 32-column units (two 16-column
+    // TMEM chunks), which are staged in shared memory and written out as 64-byte row segments =====
     const int q = warp & 3;
-    const int chunk0 = (warp - 2) >> 2;
+    const int unit0 = (warp - 2) >> 2;
     const int r = q * 32 + lane;  // row within the 128-row tile
+    uint8_t* stg = staging + (warp - 2) * STG_WARP_BYTES;
+    // staging layout: row-in-warp * 64 B + (16-byte piece ^ swizzle(row)); conflict-free for the row-wise writes and for
+    // the transposed reads (lane -> row = 8 i + lane / 4, piece = lane % 4)
+    const uint32_t stg_w = smem_u32(stg) + lane * 64;
+    const int sw_w = (lane >> 1) & 3;
+    const int t_piece = lane & 3;
+    auto chunk_at = [&](int k) { return 2 * (unit0 + EPI_WARPS_PER_QUARTER * (k >> 1)) + (k & 1); };
+    auto row_of = [&](const TileCoord& tc, int rr, long long& row, int& img, bool& valid) {
+      if (a.mode == 0) {
+        row = static_cast<long long>(tc.m0) + rr;
+        valid = row < a.M;
+        img = a.rows_per_image > 0 ? static_cast<int>(row / a.rows_per_image) : 0;
+      } else {
+        const int bx = rr % a.BW;
+        const int r2 = rr / a.BW;
+        const int by = r2 % a.BH;
+        const int bn = r2 / a.BH;
+        const int x = tc.x0 + bx, y = tc.y0 + by, n = tc.n_img0 + bn;
+        valid = (x < a.W) && (y < a.H) && (n < a.n_img);
+        row = (static_cast<long long>(n) * a.H + y) * a.W + x;
+        img = n;
+      }
+    };
+    auto stage_half = [&](int h, const uint4& o0, const uint4& o1) {  // 16 columns (32 B) of this thread's row
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg_w + (((2 * h) ^ sw_w) << 4)), "r"(o0.x), "r"(o0.y),
+                   "r"(o0.z), "r"(o0.w) : "memory");
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg_w + (((2 * h + 1) ^ sw_w) << 4)), "r"(o1.x), "r"(o1.y),
+                   "r"(o1.z), "r"(o1.w) : "memory");
+    };
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
@@ -217,59 +253,76 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       tile_coords(a, m_tile, tc);
       const int n0 = n_tile * a.block_n;
 
-      long long row;  // output row (pixel/token index)
+      long long row;  // output row (pixel/token index) of this thread's accumulator row
       int img;        // image index for the per-image row vector
       bool valid;
-      if (a.mode == 0) {
-        row = static_cast<long long>(tc.m0) + r;
-        valid = row < a.M;
-        img = a.rows_per_image > 0 ? static_cast<int>(row / a.rows_per_image) : 0;
-      } else {
-        const int bx = r % a.BW;
-        const int rr = r / a.BW;
-        const int by = rr % a.BH;
-        const int bn = rr / a.BH;
-        const int x = tc.x0 + bx, y = tc.y0 + by, n = tc.n_img0 + bn;
-        valid = (x < a.W) && (y < a.H) && (n < a.n_img);
-        row = (static_cast<long long>(n) * a.H + y) * a.W + x;
-        img = n;
+      row_of(tc, r, row, img, valid);
+      // rows this lane writes in the transposed (coalesced) store
+      long long t_row[4];
+      bool t_valid[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        int img_unused;
+        row_of(tc, q * 32 + i * 8 + (lane >> 2), t_row[i], img_unused, t_valid[i]);
       }
+      // flush one staged unit: `pieces` = 2 (one 16-column chunk) or 4; ocol = first output column of the unit
+      auto flush = [&](int pieces, int ocol) {
+        __syncwarp();
+        uint4 t[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int rw = i * 8 + (lane >> 2);
+          const uint32_t addr = smem_u32(stg) + rw * 64 + ((t_piece ^ ((rw >> 1) & 3)) << 4);
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(t[i].x), "=r"(t[i].y), "=r"(t[i].z), "=r"(t[i].w) : "r"(addr) : "memory");
+        }
+        __syncwarp();  // the next unit may overwrite the staging rows
+        if (t_piece < pieces && !(a.dbg & 32)) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (t_valid[i]) *reinterpret_cast<uint4*>(a.out + static_cast<size_t>(t_row[i]) * a.ldo + ocol + t_piece * 8) = t[i];
+        }
+      };
 
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * ACC_STRIDE + (static_cast<uint32_t>(q * 32) << 16);
 
-      // Residual / row-vector loads of chunk c+2 are issued before the TMEM wait of chunk c so that their L2/HBM latency
-      // overlaps the TMEM load and the math of the current chunk; bias (L1-resident broadcast) is loaded under the wait.
+      // Residual / row-vector loads of the next chunk are issued before the TMEM wait of the current one so that their
+      // L2/HBM latency overlaps the TMEM load and the math; bias (L1-resident broadcast) is loaded under the wait.
       if (!kGeglu) {
         const int chunks = a.block_n / 16;
+        const bool direct = a.kv_world > 0;  // fused K/V scatter keeps the direct row-wise stores
         const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
         uint4 r0 = z4, r1 = z4, v0 = z4, v1 = z4, nr0 = z4, nr1 = z4, nv0 = z4, nv1 = z4;
         const bf16* res_row = a.residual ? a.residual + static_cast<size_t>(row) * a.ld_res + n0 : nullptr;
         const bf16* rv_row = a.rowvec ? a.rowvec + static_cast<size_t>(img) * a.ld_rowvec + n0 : nullptr;
-        const bool ld_res = valid && res_row != nullptr, ld_rv = valid && rv_row != nullptr;
-        if (chunk0 < chunks) {
+        const bool ld_res = valid && res_row != nullptr && !(a.dbg & 64), ld_rv = valid && rv_row != nullptr;
+        if (chunk_at(0) < chunks) {
+          const int c0 = chunk_at(0);
           if (ld_res) {  // plain loads: the residual may alias the output (in-place add)
-            r0 = *reinterpret_cast<const uint4*>(res_row + chunk0 * 16);
-            r1 = *reinterpret_cast<const uint4*>(res_row + chunk0 * 16 + 8);
+            r0 = *reinterpret_cast<const uint4*>(res_row + c0 * 16);
+            r1 = *reinterpret_cast<const uint4*>(res_row + c0 * 16 + 8);
           }
           if (ld_rv) {
-            v0 = __ldg(reinterpret_cast<const uint4*>(rv_row + chunk0 * 16));
-            v1 = __ldg(reinterpret_cast<const uint4*>(rv_row + chunk0 * 16 + 8));
+            v0 = __ldg(reinterpret_cast<const uint4*>(rv_row + c0 * 16));
+            v1 = __ldg(reinterpret_cast<const uint4*>(rv_row + c0 * 16 + 8));
           }
         }
-        for (int c = chunk0; c < chunks; c += EPI_WARPS_PER_QUARTER) {
+        for (int k = 0;; ++k) {
+          const int c = chunk_at(k);
+          if (c >= chunks) break;
+          const int cn = chunk_at(k + 1);
           uint32_t v[16];
           tmem_ld16(taddr + c * 16, v);
           const int col = n0 + c * 16;
-          if (c + EPI_WARPS_PER_QUARTER < chunks) {
+          if (cn < chunks) {
             if (ld_res) {
-              nr0 = *reinterpret_cast<const uint4*>(res_row + (c + EPI_WARPS_PER_QUARTER) * 16);
-              nr1 = *reinterpret_cast<const uint4*>(res_row + (c + EPI_WARPS_PER_QUARTER) * 16 + 8);
+              nr0 = *reinterpret_cast<const uint4*>(res_row + cn * 16);
+              nr1 = *reinterpret_cast<const uint4*>(res_row + cn * 16 + 8);
             }
             if (ld_rv) {
-              nv0 = __ldg(reinterpret_cast<const uint4*>(rv_row + (c + EPI_WARPS_PER_QUARTER) * 16));
-              nv1 = __ldg(reinterpret_cast<const uint4*>(rv_row + (c + EPI_WARPS_PER_QUARTER) * 16 + 8));
+              nv0 = __ldg(reinterpret_cast<const uint4*>(rv_row + cn * 16));
+              nv1 = __ldg(reinterpret_cast<const uint4*>(rv_row + cn * 16 + 8));
             }
           }
           float4 b4[4];
@@ -304,7 +357,9 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             o0.z = pack_bf16x2(f[4], f[5]);   o0.w = pack_bf16x2(f[6], f[7]);
             o1.x = pack_bf16x2(f[8], f[9]);   o1.y = pack_bf16x2(f[10], f[11]);
             o1.z = pack_bf16x2(f[12], f[13]); o1.w = pack_bf16x2(f[14], f[15]);
-            if (a.kv_world > 0 && col >= a.kv_col0) {
+            if (!direct) {
+              stage_half(k & 1, o0, o1);
+            } else if (col >= a.kv_col0) {
               // fused all-gather: the K|V columns of the QKV projection go straight into every rank's gathered
               // K/V buffer (peer memory over NVLink; own rank included) at this rank's global token rows
               const long long half = row / a.kv_rows_local;
@@ -322,6 +377,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               op[1] = o1;
             }
           }
+          if (!direct && ((k & 1) || c + 1 >= chunks)) flush((k & 1) ? 4 : 2, n0 + (c & ~1) * 16);
           r0 = nr0; r1 = nr1; v0 = nv0; v1 = nv1;
         }
       } else {
@@ -329,7 +385,9 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         // n_tile*block_n/2 .. +block_n/2
         const int half = a.block_n / 2;
         const int chunks = half / 16;
-        for (int c = chunk0; c < chunks; c += EPI_WARPS_PER_QUARTER) {
+        for (int k = 0;; ++k) {
+          const int c = chunk_at(k);
+          if (c >= chunks) break;
           uint32_t va[16], vg[16];
           tmem_ld16(taddr + c * 16, va);
           tmem_ld16(taddr + half + c * 16, vg);
@@ -358,15 +416,17 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               f2_unpack(geglu2(a01, g01), o[4 * i], o[4 * i + 1]);
               f2_unpack(geglu2(a23, g23), o[4 * i + 2], o[4 * i + 3]);
             }
-            const int ocol = n_tile * half + c * 16;
-            uint4* op = reinterpret_cast<uint4*>(a.out + static_cast<size_t>(row) * a.ldo + ocol);
             uint4 o0, o1;
             o0.x = pack_bf16x2(o[0], o[1]);   o0.y = pack_bf16x2(o[2], o[3]);
             o0.z = pack_bf16x2(o[4], o[5]);   o0.w = pack_bf16x2(o[6], o[7]);
             o1.x = pack_bf16x2(o[8], o[9]);   o1.y = pack_bf16x2(o[10], o[11]);
             o1.z = pack_bf16x2(o[12], o[13]); o1.w = pack_bf16x2(o[14], o[15]);
-            op[0] = o0;
-            op[1] = o1;
+            // direct row-wise stores: this epilogue is bound by the GEGLU math, staging only adds to it (measured)
+            if (!(a.dbg & 32)) {
+              uint4* op = reinterpret_cast<uint4*>(a.out + static_cast<size_t>(row) * a.ldo + n_tile * half + c * 16);
+              op[0] = o0;
+              op[1] = o1;
+            }
           }
         }
       }

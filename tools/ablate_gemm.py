@@ -37,11 +37,12 @@ def conv(hw, cin, cout, bn):
     return t, t * 1e-6 / waves / kb * 1.965e9
 
 
-def gemm(M, N, K, bn):
+def gemm(M, N, K, bn, geglu=False, residual=False):
     a = torch.randn(M, K, device=dev).bfloat16()
     w = (torch.randn(N, K, device=dev) * 0.05).bfloat16()
     b = torch.randn(N, device=dev)
-    t = timeit(lambda: ops.gemm(a, w, b, block_n=bn))
+    res = torch.randn(M, N, device=dev).bfloat16() if residual else None
+    t = timeit(lambda: ops.gemm(a, w, b, block_n=bn, geglu=geglu, residual=res))
     tiles = (M // 128) * (N // bn)
     waves = -(-tiles // 148)
     kb = K // 64
@@ -50,7 +51,10 @@ def gemm(M, N, K, bn):
 
 abl = os.environ.get("D4D_GEMM_ABLATE", "0")
 out = [f"ablate={abl:>2s}"]
-for name, fn in [("conv L0 320 bn160", lambda: conv(64, 320, 320, 160)), ("conv L0 960 bn64", lambda: conv(64, 960, 320, 64)),
+small = [("gemm L0 qkv K320 bn240", lambda: gemm(131072, 960, 320, 240)), ("gemm L0 proj+res K320 bn160", lambda: gemm(131072, 320, 320, 160, residual=True)),
+         ("gemm L0 ff1 geglu K320 bn256", lambda: gemm(131072, 2560, 320, 256, geglu=True)), ("gemm L0 ff2+res K1280 bn160", lambda: gemm(131072, 320, 1280, 160, residual=True)),
+         ("gemm L1 qkv K640 bn240", lambda: gemm(32768, 1920, 640, 240)), ("gemm L1 ff1 geglu K640 bn256", lambda: gemm(32768, 5120, 640, 256, geglu=True))]
+for name, fn in small if "--small" in sys.argv else [("conv L0 320 bn160", lambda: conv(64, 320, 320, 160)), ("conv L0 960 bn64", lambda: conv(64, 960, 320, 64)),
                  ("conv L0 960 bn160", lambda: conv(64, 960, 320, 160)), ("conv L2 2560 bn256", lambda: conv(16, 2560, 1280, 256)),
                  ("gemm L1 ff2 bn160", lambda: gemm(32768, 640, 2560, 160)), ("gemm L1 ff2 bn64", lambda: gemm(32768, 640, 2560, 64)),
                  ("gemm L2 ff2 bn256", lambda: gemm(8192, 1280, 5120, 256))]:
