@@ -77,6 +77,20 @@ def test_gemm_epilogues(cuda):
     _close(out, a.float() @ w.float().t())
 
 
+@pytest.mark.parametrize("M,N,K,bn", [(333, 240, 128, 240), (77, 48, 64, 48), (513, 400, 64, 80), (200, 96, 64, 32),
+                                      (129, 320, 192, 160), (1, 16, 64, 16)])
+def test_gemm_staged_epilogue_tails(cuda, M, N, K, bn):
+    """The epilogue stages 32-column units (two 16-column TMEM chunks) per warp and stores 64-byte row segments: odd chunk
+    counts per tile (240, 48, 80 columns), ragged M (rows past M must not be written) and the in-place residual."""
+    from diffuman4d_b200 import ops
+    a, w = _rand((M, K), 25), _rand((N, K), 26, std=K ** -0.5)
+    bias = torch.randn(N, generator=torch.Generator().manual_seed(27)).cuda()
+    res = _rand((M, N), 28)
+    ref = a.float() @ w.float().t() + bias
+    _close(ops.gemm(a, w, bias, block_n=bn), ref)
+    _close(ops.gemm(a, w, bias, residual=res, block_n=bn), ref + res.float())
+
+
 def test_gemm_two_source(cuda):
     from diffuman4d_b200 import ops
     M, N, K1, K2 = 512, 320, 640, 320
