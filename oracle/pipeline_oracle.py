@@ -7,8 +7,15 @@ Restates  PIPE = /root/reference/src/diffusers/pipelines/diffuman4d/pipeline_dif
   * ``__call__`` denoise loop           PIPE:345-425  (input assembly, CFG, per-frame scheduler step)
   * ``sliding_iterative_denoise``       PIPE:463-551  (window schedule + invariants)
 and upstream diffusers==0.33.1 ``DDIMScheduler`` (set_timesteps / step, eta=0), which the
-reference deep-copies per frame (PIPE:265-271).  The scheduler class of the shipped checkpoint is
-not in the repo; DDIM (SD-2.x default) is assumed -- **parity unpinned**, see DESIGN.md.
+reference deep-copies per frame (PIPE:265-271).
+
+PARITY STATUS: the pipeline logic is pinned against the reference's OWN ``Diffuman4DPipeline.__call__`` and
+``sliding_iterative_denoise`` executed on stubs of the upstream plumbing (tests/golden/gen_golden.py::gen_pipeline ->
+tests/golden/pipeline_ref.pt; tests/test_oracle.py): input assembly, CFG negatives, cond-frame aliasing, per-frame
+stepping (epsilon and v-prediction), visited windows, timestep bookkeeping and the three ValueError texts all match.
+The scheduler ARITHMETIC is not: the scheduler class of the shipped checkpoint is not in the repo and diffusers is not
+installed; DDIM (SD-2.x default) is restated from the published 0.33.1 source -- **parity unpinned** for that class, see
+DESIGN.md.
 
 The VAE is outside the hot path and is not restated: all functions take latents.
 """

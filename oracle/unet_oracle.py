@@ -5,13 +5,20 @@ delegates to.  Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s
 cpu_baseline / ``--impl reference`` legs may import this module.
 
 PARITY STATUS: the reference has no tests, golden vectors or fixtures for this path, and
-its arithmetic lives in the un-vendored dependency ``diffusers==0.33.1`` (pinned in
-/root/reference/requirements.txt:5) which is not installed here (no network).  The upstream
-semantics are therefore restated from the published 0.33.1 sources, anchored on the
-reference's own call sites.  What IS pinned against code run from /root/reference
-(tests/golden/gen_golden.py): ``PoseEncoder`` (imported directly) and the 3-D token reshape of
-``MultiviewTransformerBlock.forward`` (the reference's own forward running on a stubbed
-upstream base class).  Everything else: **parity unpinned** (see DESIGN.md).
+its leaf arithmetic lives in the un-vendored dependency ``diffusers==0.33.1`` (pinned in
+/root/reference/requirements.txt:5) which is not installed here (no network).  Pinned against
+code RUN from /root/reference (tests/golden/gen_golden.py, fixtures committed, tests in
+tests/test_oracle.py):
+  * the whole UNet wiring -- the reference's own ``UNetMultiviewConditionModel`` constructor and
+    forward, its block classes, ``TransformerMultiviewModel``, ``MultiviewTransformerBlock`` and
+    ``PoseEncoder`` executed on stubs of the upstream LEAF classes only (three configurations,
+    spatial+CFG and temporal inputs, max deviation < 2e-4), including the diffusers key layout
+    (``load_state_dict(strict=True)`` of the product's key/shape spec into the reference model);
+  * ``PoseEncoder`` and ``MultiviewTransformerBlock.forward`` individually.
+Still **parity unpinned**: the arithmetic INSIDE the upstream leaf classes (ResnetBlock2D,
+Down/Upsample2D, Transformer2DModel helpers, BasicTransformerBlock constructor, Attention +
+AttnProcessor2_0, GEGLU, Timesteps, TimestepEmbedding), restated here from the published 0.33.1
+sources and anchored on the reference's call sites.
 
 Module tree and ``state_dict`` keys follow the diffusers layout so a real checkpoint
 (`unet/diffusion_pytorch_model.safetensors`) loads by name.
