@@ -447,10 +447,20 @@ def gen_unet():
     torch.save(out, f"{HERE}/unet_ref.pt")
 
 
-def gen_pipeline():
-    """Run the reference pipeline class on stubs; see the module docstring."""
+_RANDN_CALLS = [0]
+
+
+def _counter_randn(shape, generator=None, device=None, dtype=None):
+    """stand-in for diffusers.utils.torch_utils.randn_tensor: the k-th call draws from Generator(9000 + k), so the tests can
+    reproduce the initial noise of every task (only sliding_iterative_denoise with latents=None reaches it, PIPE:175)."""
+    g = torch.Generator().manual_seed(9000 + _RANDN_CALLS[0])
+    _RANDN_CALLS[0] += 1
+    return torch.randn(tuple(shape), generator=g).to(dtype=dtype)
+
+
+def _load_ref_pipeline():
+    """The reference pipeline module on stubs of the upstream plumbing -> (module, make_pipe)."""
     import contextlib
-    import copy
 
     from diffuman4d_b200.config import SchedulerConfig
     from oracle.pipeline_oracle import DDIMOracle
@@ -473,6 +483,8 @@ def gen_pipeline():
         @property
         def _execution_device(self):
             return torch.device("cpu")
+
+        device = torch.device("cpu")  # DiffusionPipeline.device (read by SAMP:177)
 
         @contextlib.contextmanager
         def progress_bar(self, total=None):
@@ -500,7 +512,7 @@ def gen_pipeline():
         "diffusers.schedulers": {"KarrasDiffusionSchedulers": object},
         "diffusers.utils": {"logging": types.SimpleNamespace(get_logger=_logging.getLogger),
                             "replace_example_docstring": lambda doc: (lambda f: f)},
-        "diffusers.utils.torch_utils": {"randn_tensor": None},
+        "diffusers.utils.torch_utils": {"randn_tensor": _counter_randn},
         "diffusers.pipelines": {},
         "diffusers.pipelines.pipeline_utils": {"DiffusionPipeline": StubDiffusionPipeline,
                                                "StableDiffusionMixin": type("StableDiffusionMixin", (_Mixin,), {})},
@@ -558,6 +570,12 @@ def gen_pipeline():
         sc = SchedulerConfig(prediction_type=prediction_type)
         return pipe_mod.Diffuman4DPipeline(FakeVAE(), UNetAdapter(cin, pose), RefScheduler(sc)), cin
 
+    return pipe_mod, make_pipe
+
+
+def gen_pipeline():
+    """Run the reference pipeline class on stubs; see the module docstring."""
+    pipe_mod, make_pipe = _load_ref_pipeline()
     out = {"cases": {}}
     h = w = 8
     g = torch.Generator().manual_seed(2024)
@@ -643,7 +661,81 @@ def gen_pipeline():
     torch.save(out, f"{HERE}/pipeline_ref.pt")
 
 
+def gen_sampler():
+    """Drive the reference's ``SlidingIterativeSampler`` (src/samplers/sliding_iterative_sampler.py) -- its task lists,
+    sample loading, grid bookkeeping -- with the reference pipeline-on-stubs above and the synthetic dataset."""
+    pipe_mod, make_pipe = _load_ref_pipeline()
+    sys.path.insert(0, HERE)
+    from synthetic_dataset import SyntheticSpaTemDataset
+    import logging as _logging
+
+    saved = []
+
+    class RankedLogger:
+        def __init__(self, *a, **k):
+            self._l = _logging.getLogger("ref")
+
+        def __getattr__(self, name):
+            return getattr(self._l, name)
+
+    mods = {"src": {}, "src.data": {}, "src.data.spatem_dataset": {"SpaTemDataset": object},
+            "src.diffusers": {}, "src.diffusers.pipelines": {}, "src.diffusers.pipelines.diffuman4d": {},
+            "src.diffusers.pipelines.diffuman4d.pipeline_diffuman4d": {"Diffuman4DPipeline": pipe_mod.Diffuman4DPipeline},
+            "src.samplers": {}, "src.samplers.utils": {},
+            "src.samplers.utils.sampling_utils": {
+                "save_sampling_results": lambda sample, output_dir=None: saved.append(
+                    {"alt": sample["alt"], "domain": sample["domain"], "domain_label": sample["domain_label"],
+                     "labels": list(sample["labels"]), "timestep_indices": sample["timestep_indices"].clone(),
+                     "fully_denoised": sample["fully_denoised"].clone()}),
+                "check_sampling_results": lambda *a, **k: True},
+            "src.utils": {"RankedLogger": RankedLogger}}
+    for name, attrs in mods.items():
+        m = types.ModuleType(name)
+        m.__path__ = []
+        for k, v in attrs.items():
+            setattr(m, k, v)
+        sys.modules[name] = m
+    samp_mod = load_by_path("src.samplers.sliding_iterative_sampler", f"{REF}/src/samplers/sliding_iterative_sampler.py")
+
+    out = {"cases": {}}
+    for tag, kw in (("v6_t4_stride1", dict(spa_label_range=[0, 6, 1], tem_label_range=[0, 4, 1], input_spa_labels=[1, 4],
+                                           window_size=2, sliding_stride=1, bidirectional=True, alternation_rounds=3)),
+                    ("v5_t2_stride2_unidir", dict(spa_labels=[0, 2, 3, 5, 7], tem_labels=[3, 9], input_spa_labels=[2],
+                                                   window_size=2, sliding_stride=2, bidirectional=False, alternation_rounds=2))):
+        saved.clear()
+        _RANDN_CALLS[0] = 0
+        n_cams = 8
+        pipe, _ = make_pipe(True)
+        sampler = samp_mod.SlidingIterativeSampler(dataset=SyntheticSpaTemDataset(n_cams), pipelines=[pipe], output_dir=None,
+                                                   num_denoising_steps=1, guidance_scale=2.0, sliding_shift=0, **kw)
+        sampler.execute_tasks()
+        grid = {(s, t): sampler.latents[s][t].clone() for s in sampler.spa_labels for t in sampler.tem_labels}
+        ti = {(s, t): int(sampler.timestep_indices[s][t]) for s in sampler.spa_labels for t in sampler.tem_labels}
+        out["cases"][tag] = {"kwargs": kw, "n_cams": n_cams, "all_tasks": sampler.all_tasks, "grid_latents": grid,
+                             "grid_timestep_indices": ti, "saved": list(saved)}
+        print("sampler", tag, len(saved), "tasks", sorted(set(ti.values())),
+              float(torch.stack(list(grid.values())).abs().mean()))
+    # the constructor's argument checks (SAMP:72-90)
+    errs = {}
+    for tag, kw in (("window_gt_targets", dict(spa_label_range=[0, 4, 1], input_spa_labels=[1], window_size=4)),
+                    ("targets_mod_stride", dict(spa_label_range=[0, 6, 1], input_spa_labels=[1], window_size=2, sliding_stride=2)),
+                    ("tems_mod_stride", dict(spa_label_range=[0, 6, 1], input_spa_labels=[1, 4], tem_label_range=[0, 3, 1],
+                                             window_size=2, sliding_stride=2)),
+                    ("window_gt_tems", dict(spa_label_range=[0, 6, 1], input_spa_labels=[1, 4], tem_label_range=[0, 1, 1],
+                                            window_size=2, alternation_rounds=2)),
+                    ("no_spa", dict(spa_label_range=None, spa_labels=None))):
+        try:
+            samp_mod.SlidingIterativeSampler(dataset=None, pipelines=[], **{"tem_label_range": [0, 4, 1], **kw})
+            errs[tag] = None
+        except ValueError as e:
+            errs[tag] = str(e)
+        print("sampler error", tag, "->", errs[tag])
+    out["errors"] = errs
+    torch.save(out, f"{HERE}/sampler_ref.pt")
+
+
 if __name__ == "__main__":
+    gen_sampler()
     gen_unet()
     gen_pipeline()
     gen_pose_encoder()

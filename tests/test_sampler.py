@@ -1,0 +1,119 @@
+"""CPU tests of ``diffuman4d_b200.sampler`` (device-resident V x T grid) against the reference's own
+``SlidingIterativeSampler`` run end to end on stubs (tests/golden/gen_golden.py::gen_sampler -> golden/sampler_ref.pt),
+plus the 2-rank (gloo) round exchange."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from diffuman4d_b200.config import SchedulerConfig
+from diffuman4d_b200.sampler import B200SlidingIterativeSampler
+from oracle.pipeline_oracle import DDIMOracle, sliding_iterative_denoise_oracle
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+sys.path.insert(0, GOLD)
+from fake_unet import make_fake_unet  # noqa: E402
+from synthetic_dataset import SyntheticSpaTemDataset  # noqa: E402
+
+
+class OraclePipeline:
+    """``sliding_iterative_denoise`` (PIPE:439-559) on the oracle, with the stand-ins the golden generator gave the
+    reference pipeline: fake UNet, 8x-average-pooling "VAE", identity decode, k-th noise draw from Generator(9000 + k)."""
+
+    def __init__(self, noise: str = "counter"):
+        self.noise, self.calls = noise, 0
+        self.unet = make_fake_unet(11)
+
+    def sliding_iterative_denoise(self, pixel_values, plucker_embeds, skeletons, cond_masks, latents, domain,
+                                  timestep_indices, window_size, sliding_stride, sliding_shift, bidirectional,
+                                  num_denoising_steps, alternation_rounds, guidance_scale, **kw):
+        z = F.avg_pool2d(pixel_values, 8)
+        pix = torch.cat([z, z.mean(dim=1, keepdim=True)], dim=1)
+        h, w = pix.shape[-2:]
+        mask = F.interpolate(cond_masks, size=(h, w), mode="nearest")
+        if latents is None:
+            seed = 9000 + self.calls if self.noise == "counter" else int(pixel_values.abs().sum().item() * 1000) % (2 ** 31)
+            self.calls += 1
+            latents = torch.randn((len(pix), 4, h, w), generator=torch.Generator().manual_seed(seed))
+        out = sliding_iterative_denoise_oracle(
+            self.unet, DDIMOracle(SchedulerConfig()), pixel_latents=pix, plucker=plucker_embeds, skeletons=skeletons,
+            cond_mask=mask, latents=latents, domain=domain, timestep_indices=timestep_indices.cpu(), window_size=window_size,
+            sliding_stride=sliding_stride, sliding_shift=sliding_shift, bidirectional=bidirectional,
+            num_denoising_steps=num_denoising_steps, alternation_rounds=alternation_rounds, guidance_scale=guidance_scale,
+            enable_pose_encoder=True)
+        out["images"] = out["latents"]
+        return out
+
+
+def _make(kwargs, n_cams, pipe, save_fn=None):
+    return B200SlidingIterativeSampler(dataset=SyntheticSpaTemDataset(n_cams), pipelines=[pipe], output_dir=None,
+                                       num_denoising_steps=1, guidance_scale=2.0, sliding_shift=0, save_fn=save_fn, **kwargs)
+
+
+@pytest.mark.parametrize("tag", ["v6_t4_stride1", "v5_t2_stride2_unidir"])
+def test_sampler_matches_reference_sampler_golden(tag):
+    c = torch.load(os.path.join(GOLD, "sampler_ref.pt"))["cases"][tag]
+    saved = []
+    s = _make(c["kwargs"], c["n_cams"], OraclePipeline(), save_fn=lambda sample, out_dir: saved.append(sample))
+    assert s.all_tasks == c["all_tasks"]                                  # SAMP:192-199
+    s.execute_tasks()
+    for (spa, tem), ref in c["grid_latents"].items():                     # final grid == the reference's dict of latents
+        torch.testing.assert_close(s.latent(spa, tem), ref, rtol=1e-5, atol=1e-5)
+        assert s.timestep_index(spa, tem) == c["grid_timestep_indices"][(spa, tem)]
+    assert len(saved) == len(c["saved"])
+    for got, ref in zip(saved, c["saved"]):                               # per task: order, labels, bookkeeping
+        assert (got["alt"], got["domain"], got["domain_label"]) == (ref["alt"], ref["domain"], ref["domain_label"])
+        assert [tuple(x) for x in got["labels"]] == [tuple(x) for x in ref["labels"]]
+        assert torch.equal(got["timestep_indices"].cpu(), ref["timestep_indices"])
+        assert torch.equal(got["fully_denoised"].cpu(), ref["fully_denoised"])
+
+
+def test_sampler_argument_errors_match_reference_messages():
+    errs = torch.load(os.path.join(GOLD, "sampler_ref.pt"))["errors"]
+    cases = {"window_gt_targets": dict(spa_label_range=[0, 4, 1], input_spa_labels=[1], window_size=4),
+             "targets_mod_stride": dict(spa_label_range=[0, 6, 1], input_spa_labels=[1], window_size=2, sliding_stride=2),
+             "tems_mod_stride": dict(spa_label_range=[0, 6, 1], input_spa_labels=[1, 4], tem_label_range=[0, 3, 1],
+                                     window_size=2, sliding_stride=2),
+             "window_gt_tems": dict(spa_label_range=[0, 6, 1], input_spa_labels=[1, 4], tem_label_range=[0, 1, 1],
+                                    window_size=2, alternation_rounds=2),
+             "no_spa": dict(spa_label_range=None, spa_labels=None)}
+    for tag, kw in cases.items():
+        assert errs[tag] is not None
+        with pytest.raises(ValueError) as e:
+            B200SlidingIterativeSampler(dataset=None, pipelines=[], **{"tem_label_range": [0, 4, 1], **kw})
+        assert str(e.value) == errs[tag]
+
+
+def _rank_main(rank, world, port, kwargs, n_cams, q):
+    import torch.distributed as dist
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    s = _make(kwargs, n_cams, OraclePipeline(noise="content"))
+    s.execute_tasks(rank=rank, world=world)
+    q.put((rank, s.grid_latents.tolist(), s.grid_timestep_indices.tolist()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sampler_two_ranks_equal_single_process():
+    """Round-sharded tasks + one all-gather of the updated cells per round (gloo, world_size 2) reproduce the
+    single-process grid on every rank."""
+    import torch.multiprocessing as mp
+    kwargs = dict(spa_label_range=[0, 6, 1], tem_label_range=[0, 4, 1], input_spa_labels=[1, 4], window_size=2,
+                  sliding_stride=1, bidirectional=False, alternation_rounds=2)
+    single = _make(kwargs, 8, OraclePipeline(noise="content"))
+    single.execute_tasks()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 400
+    procs = [ctx.Process(target=_rank_main, args=(r, 2, port, kwargs, 8, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, lat, ti in results:
+        torch.testing.assert_close(torch.tensor(lat), single.grid_latents, rtol=1e-5, atol=1e-5)
+        assert torch.tensor(ti).equal(single.grid_timestep_indices)
