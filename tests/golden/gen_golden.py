@@ -147,7 +147,9 @@ def gen_plucker():
         import inspect
         print("calc_plucker_embeds signature:", inspect.signature(ray.calc_plucker_embeds))
         raise
-    torch.save({"K": Ks, "c2w": c2ws, "plucker": pl}, f"{HERE}/plucker.pt")
+    rel = ray.calc_relative_poses(c2ws)                      # what the dataset feeds the embedding (DATA:162-165)
+    pl_rel = ray.calc_plucker_embeds(h, w, Ks, rel)
+    torch.save({"K": Ks, "c2w": c2ws, "plucker": pl, "rel_poses": rel, "plucker_rel": pl_rel}, f"{HERE}/plucker.pt")
     print("plucker", tuple(pl.shape), float(pl.min()), float(pl.max()))
 
 

@@ -134,3 +134,15 @@ def test_loader_config_mapping():
                                     "beta_end": 0.012, "clip_sample": False, "set_alpha_to_one": False, "steps_offset": 1,
                                     "prediction_type": "v_prediction"})
     assert s.prediction_type == "v_prediction" and s.steps_offset == 1
+
+
+def test_plucker_embeds_match_reference_ray_utils():
+    """diffuman4d_b200.rays against ``calc_plucker_embeds`` / ``calc_relative_poses`` run from the reference
+    (src/data/utils/ray_utils.py:101-118; fixture tests/golden/plucker.pt)."""
+    import os
+    from diffuman4d_b200.rays import plucker_embeds, relative_poses
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "plucker.pt"))
+    torch.testing.assert_close(plucker_embeds(16, 16, g["K"], g["c2w"]), g["plucker"], rtol=1e-5, atol=2e-6)
+    rel = relative_poses(g["c2w"])
+    torch.testing.assert_close(rel, g["rel_poses"], rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(plucker_embeds(16, 16, g["K"], rel), g["plucker_rel"], rtol=1e-5, atol=5e-6)
