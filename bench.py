@@ -9,8 +9,12 @@ weights of the real architecture (no network for the checkpoint).
 
     python bench.py --gpus 1 --steps 10 --warmup 3
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...   (weak scaling: every
-        rank denoises its own window; windows of one sampler round are independent units)
-    python bench.py --impl reference ...   (the CPU oracle -- the reference's torch graph restated -- on host cores)
+        rank denoises its own window; windows of one sampler round are independent units, SURVEY.md section 8e.1;
+        the line also carries a `sharded` object: ONE window frame-sharded over the N ranks)
+    python bench.py --impl reference ...   (the CPU oracle -- the reference's torch graph restated -- on host cores,
+        REAL W16 window steps, as many of the requested --steps as fit the time budget)
+
+Everything printed is measured in this run; figures that come from a committed profile name the file they were read from.
 """
 from __future__ import annotations
 
@@ -18,6 +22,7 @@ import argparse
 import ctypes as C
 import json
 import os
+import re
 import subprocess
 import sys
 import threading
@@ -30,10 +35,15 @@ sys.path.insert(0, ROOT)
 
 WORKLOAD = dict(name="demo_4d_tiny spatial window W16 (4 cond + 12 target frames), CFG 2.0, latents 64x64",
                 F=16, n_cond=4, h=64, w=64, guidance=2.0, domain="spatial", n_steps=18)
-# bounded samples of the same window step for the CPU arm (largest that fits the time budget is used)
-CPU_SAMPLES = [dict(F=4, n_cond=1, h=64, w=64), dict(F=2, n_cond=1, h=64, w=64), dict(F=2, n_cond=1, h=32, w=32)]
+# other BASELINE configurations, timed at N=1 as `also` entries (not the headline)
+ALSO = [dict(key="W24_temporal_64", name="temporal window W24 (12 cond + 12 target frames), CFG 2.0, latents 64x64",
+             F=24, n_cond=12, h=64, w=64, domain="temporal", steps=5),
+        dict(key="W16_spatial_128", name="spatial window W16, CFG 2.0, latents 128x128 (reference default, 1024^2 px)",
+             F=16, n_cond=4, h=128, w=128, domain="spatial", steps=3)]
 METRIC = "unet_window_denoise_steps_per_sec"
 UNIT = "window-steps/s"
+# ncu --set full capture of the dominant kernel (tools/gpu_profile.sh -> tools/ncu_summary.py); parsed at run time
+NCU_SUMMARIES = ["profiles/r02_ncu_attention.txt", "profiles/r01d_ncu_attention.txt"]
 
 
 def synth_inputs(F, n_cond, h, w, pose=True, seed=0):
@@ -81,6 +91,25 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.samples)}
 
 
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, read from the newest committed ncu summary
+    (never a literal): returns (bytes, file) or (None, None)."""
+    for rel in NCU_SUMMARIES:
+        path = os.path.join(ROOT, rel)
+        if not os.path.exists(path):
+            continue
+        tot, found = 0.0, 0
+        for line in open(path):
+            m = re.match(r"\s*dram__bytes_(read|write)\.sum\s+([0-9.]+)\s+(\w+)", line)
+            if m and found < 2:   # first kernel block of the file
+                mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(m.group(3), 1.0)
+                tot += float(m.group(2)) * mult
+                found += 1
+        if found == 2:
+            return int(tot), rel
+    return None, None
+
+
 # ------------------------------------------------------------------------------------------------------- CPU arm
 def calibrate_cpu_threads():
     """Pick the torch thread count that maximises fp32 conv throughput on this host (a cgroup-limited box can be much
@@ -107,53 +136,51 @@ def calibrate_cpu_threads():
     return best
 
 
-def cpu_oracle_window_seconds(repeats: int, warmup: int, budget_s: float):
-    """Times the oracle (test infrastructure, used here ONLY as the reported CPU baseline) on a bounded sample of the
-    window step chosen so that (warmup + repeats) steps fit in ``budget_s``."""
+def cpu_oracle_w16_steps(max_steps: int, budget_s: float):
+    """Times the oracle (test infrastructure, used here ONLY as the reported CPU baseline) on REAL window steps of the
+    benchmark workload (W16 @ 64x64, 32 images, 31.94 TFLOP each): as many of ``max_steps`` as fit ``budget_s`` after the
+    first one, never fewer than one.  No FLOP scaling.  Returns (seconds per step list, threads)."""
     from diffuman4d_b200.config import SchedulerConfig, UNetConfig
-    from diffuman4d_b200.flops import unet_flops
     from diffuman4d_b200.weights import random_state_dict
     from oracle.pipeline_oracle import DDIMOracle, denoise_window_oracle
     from oracle.unet_oracle import OracleUNet
-    threads, conv_gflops = calibrate_cpu_threads()
+    threads, _ = calibrate_cpu_threads()
     cfg = UNetConfig.sd21()
-    per_step = budget_s / max(1, warmup + repeats)
-    s = CPU_SAMPLES[-1]
-    for cand in CPU_SAMPLES:
-        est = unet_flops(cfg, 2 * cand["F"], cand["F"], cand["h"], cand["w"])["total"] / (0.6 * conv_gflops * 1e9)
-        if est <= per_step:
-            s = cand
-            break
+    wl = WORKLOAD
     net = OracleUNet(cfg).eval()
     net.load_state_dict({k: v.float() for k, v in random_state_dict(cfg, seed=1).items()})
-    d = synth_inputs(s["F"], s["n_cond"], s["h"], s["w"])
+    d = synth_inputs(wl["F"], wl["n_cond"], wl["h"], wl["w"])
     sched = DDIMOracle(SchedulerConfig())
-    sched.set_timesteps(WORKLOAD["n_steps"])
+    sched.set_timesteps(wl["n_steps"])
 
     def unet(x, t, sk, doms, nf):
         with torch.no_grad():
             return net(x, t, sk, doms, nf)
 
     times = []
-    for i in range(warmup + repeats):
+    t_start = time.perf_counter()
+    while len(times) < max(1, max_steps):
         t0 = time.perf_counter()
         denoise_window_oracle(unet, sched, latents=d["latents"].clone(), pixel_latents=d["pixel"], plucker=d["plucker"],
-                              skeletons=d["skel"], cond_mask=d["mask"], timestep_indices=d["ts"], domain="spatial",
-                              guidance_scale=WORKLOAD["guidance"])
-        if i >= warmup:
-            times.append(time.perf_counter() - t0)
-    fl_s = unet_flops(cfg, 2 * s["F"], s["F"], s["h"], s["w"])["total"]
-    fl_w = unet_flops(cfg, 2 * WORKLOAD["F"], WORKLOAD["F"], WORKLOAD["h"], WORKLOAD["w"])["total"]
-    return times, fl_s, fl_w, threads, s
+                              skeletons=d["skel"], cond_mask=d["mask"], timestep_indices=d["ts"], domain=wl["domain"],
+                              guidance_scale=wl["guidance"])
+        times.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_start + times[-1] > budget_s:
+            break
+    return times, threads
 
 
-def cpu_baseline_obj(times, fl_s, fl_w, threads, s):
+def cpu_baseline_obj(times, threads, requested):
+    from diffuman4d_b200.config import UNetConfig
+    from diffuman4d_b200.flops import unet_flops
+    wl = WORKLOAD
+    fl = unet_flops(UNetConfig.sd21(), 2 * wl["F"], wl["F"], wl["h"], wl["w"])["total"]
     sec = sum(times) / len(times)
-    return {"value": (fl_s / sec) / fl_w, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": (f"oracle fp32, one window step with F={s['F']} frames ({s['n_cond']} cond) CFG at "
-                       f"{s['h']}x{s['w']} latents = {fl_s / 1e12:.2f} TFLOP in {sec:.2f} s ({threads} torch threads, calibrated); "
-                       f"scaled to the W16 step ({fl_w / 1e12:.2f} TFLOP) by FLOP ratio"),
-            "gflops": fl_s / sec / 1e9}
+    return {"value": 1.0 / sec, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": (f"oracle (fp32 torch restatement of the reference graph; diffusers itself is not installable here): "
+                       f"{len(times)} REAL W16@64x64 window step(s) of {requested} requested, {fl / 1e12:.2f} TFLOP each, "
+                       f"{sec:.2f} s/step on {threads} torch threads (calibrated); no FLOP scaling"),
+            "steps_timed": len(times), "same_config": True, "gflops": fl / sec / 1e9}
 
 
 def run_reference(args):
@@ -161,14 +188,17 @@ def run_reference(args):
     if rank != 0:
         return
     t0 = time.perf_counter()
-    times, fl_s, fl_w, threads, smp = cpu_oracle_window_seconds(args.steps, args.warmup, budget_s=150.0)
-    cb = cpu_baseline_obj(times, fl_s, fl_w, threads, smp)
+    times, threads = cpu_oracle_w16_steps(args.steps, budget_s=170.0)
+    cb = cpu_baseline_obj(times, threads, args.steps)
     val = cb["value"]
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 / val, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD["name"], "note": "CPU torch restatement of the reference graph (diffusers is not installable here)"},
+        "config": {"workload": WORKLOAD["name"],
+                   "note": "CPU-port baseline: the oracle's torch graph (the reference's graph restated; diffusers is not "
+                           "installable here) on the host cores, full W16 window steps; NOT the upstream bf16-GPU pipeline",
+                   "steps_timed": len(times)},
         "cpu_baseline": cb, "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": time.perf_counter() - t0}))
 
@@ -193,55 +223,71 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     if not os.path.exists(os.path.join(ROOT, "diffuman4d_b200", "libd4d.so")):
-        d4d_build.build()
+        d4d_build.build(test_lib=False)
     dev = torch.device("cuda", local)
     cfg = UNetConfig.sd21()
     wl = WORKLOAD
     F, h, w = wl["F"], wl["h"], wl["w"]
-    unet = B200MultiviewUNet(cfg, local).load_state_dict(random_state_dict(cfg, seed=1))
+    sd = random_state_dict(cfg, seed=1)
+    unet = B200MultiviewUNet(cfg, local).load_state_dict(sd)
     pipe = B200Diffuman4DPipeline(unet, SchedulerConfig())
     pipe.parepare_schedulers(wl["n_steps"], F)
-    sharded = args.mode == "sharded" and world > 1
-    full_inputs = synth_inputs(F, wl["n_cond"], h, w, seed=0 if sharded else rank)
-    F_total = F
-    sh = None
-    if sharded:   # one window, frames split over the ranks, fused K/V exchange over peer memory
-        from diffuman4d_b200.sharded import FrameShardedPipeline
-        sh = FrameShardedPipeline(pipe, max_frames=F_total, h=h, w=w)
-        lo, hi = sh.frames(F_total)
-        full_inputs = {k: v[lo:hi].contiguous() for k, v in full_inputs.items()}
-        F = hi - lo
-    host = {k: (v.to(torch.bfloat16) if v.dtype.is_floating_point else v).pin_memory()
-            for k, v in full_inputs.items()}
-    devt = {k: v.to(dev) for k, v in host.items()}
-    lat, ts = devt["latents"].clone(), devt["ts"].clone()
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:  # noqa: BLE001
+        pass
+    peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def window_step(latents, pixel, plucker, skel, mask, tsi):
-        if sh is not None:
-            sh.denoise_window(latents=latents, pixel_values_latents=pixel, plucker_embeds_latents=plucker,
-                              skeletons_latents=skel, cond_masks_latents=mask, timestep_indices=tsi, domain=wl["domain"],
-                              guidance_scale=wl["guidance"], F_total=F_total)
-        else:
-            pipe.denoise_window(latents=latents, pixel_values_latents=pixel, plucker_embeds_latents=plucker,
-                                skeletons_latents=skel, cond_masks_latents=mask, timestep_indices=tsi,
-                                domain=wl["domain"], guidance_scale=wl["guidance"])
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        barrier()
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
 
-    def step_resident():
-        lat.copy_(devt["latents"])
-        ts.copy_(devt["ts"])
-        window_step(lat, devt["pixel"], devt["plucker"], devt["skel"], devt["mask"], ts)
+    def make_stepper(p, inputs, domain, shard=None, F_total=None):
+        """Resident-input window step: restores latents / indices from device copies, then ONE public denoise_window call."""
+        devt = {k: (v.to(torch.bfloat16) if v.dtype.is_floating_point else v).to(dev) for k, v in inputs.items()}
+        lat, ts = devt["latents"].clone(), devt["ts"].clone()
+
+        def step():
+            lat.copy_(devt["latents"])
+            ts.copy_(devt["ts"])
+            kw = dict(latents=lat, pixel_values_latents=devt["pixel"], plucker_embeds_latents=devt["plucker"],
+                      skeletons_latents=devt["skel"], cond_masks_latents=devt["mask"], timestep_indices=ts, domain=domain,
+                      guidance_scale=wl["guidance"])
+            if shard is not None:
+                shard.denoise_window(F_total=F_total, **kw)
+            else:
+                p.denoise_window(**kw)
+        return step, lat, ts
+
+    # ================= headline: replicas (N=1: the single window) =================
+    full_inputs = synth_inputs(F, wl["n_cond"], h, w, seed=rank)
+    host = {k: (v.to(torch.bfloat16) if v.dtype.is_floating_point else v).pin_memory() for k, v in full_inputs.items()}
+    step_resident, lat_res, _ = make_stepper(pipe, full_inputs, wl["domain"])
 
     out_host = torch.empty_like(host["latents"]).pin_memory()
     ts_host = torch.empty_like(host["ts"]).pin_memory()
     # e2e = the public call fed from pinned HOST buffers: every step uploads its own inputs (H2D) and reads its result
     # back (D2H).  The upload of step i+1 is issued on a copy stream while step i computes (double-buffered staging), as
     # a caller streaming windows through the pipeline would do; each step still ends with a stream synchronisation.
-    stages = [{k: torch.empty_like(v) for k, v in devt.items()} for _ in range(2)]
+    stages = [{k: torch.empty_like(v, device=dev) for k, v in host.items()} for _ in range(2)]
     copy_stream = torch.cuda.Stream(device=dev)
     h2d_done = [torch.cuda.Event(), torch.cuda.Event()]
     e2e_state = {"i": 0, "primed": False}
@@ -262,27 +308,13 @@ def run_ours(args):
         upload(cur ^ 1)                                   # inputs of the NEXT step, overlapped with this step's compute
         torch.cuda.current_stream().wait_event(h2d_done[cur])
         st = stages[cur]
-        window_step(st["latents"], st["pixel"], st["plucker"], st["skel"], st["mask"], st["ts"])
+        pipe.denoise_window(latents=st["latents"], pixel_values_latents=st["pixel"], plucker_embeds_latents=st["plucker"],
+                            skeletons_latents=st["skel"], cond_masks_latents=st["mask"], timestep_indices=st["ts"],
+                            domain=wl["domain"], guidance_scale=wl["guidance"])
         out_host.copy_(st["latents"], non_blocking=True)
         ts_host.copy_(st["ts"], non_blocking=True)
         torch.cuda.current_stream().synchronize()
         e2e_state["i"] = i + 1
-
-    def timed(fn, steps, warmup):
-        for _ in range(warmup):
-            fn()
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
-            fn()
-        e1.record()
-        torch.cuda.synchronize()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        barrier()
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return ms.item()
 
     sampler = ClockSampler(local)
     sampler.start()
@@ -291,8 +323,7 @@ def run_ours(args):
     ms_e2e = timed(step_e2e, args.steps, 1)
     assert torch.isfinite(out_host.float()).all(), "non-finite latents out of the window step"
 
-    # ---- live per-kernel-kind device times of the UNet forward (CUDA events around every launch) ----
-    F = F_total        # the profile below always runs the full single-GPU window
+    # ---- live per-kernel-kind device times of the UNet forward (CUDA events around every launch; N=1 plan) ----
     B = 2 * F
     x = torch.randn(B, cfg.in_channels, h, w, device=dev).to(torch.bfloat16)
     tt = torch.randint(0, 1000, (B,), device=dev)
@@ -309,62 +340,148 @@ def run_ours(args):
         if i > 0:
             acc = [a + m for a, m in zip(acc, ms_k)]
     kind_ms = [a / reps for a in acc]
+    del x, skp, sk, y
     fl = unet_flops(cfg, B, F, h, w)
     alg = {0: fl["linear"] + fl["ff"], 1: fl["conv3x3"], 2: fl["attn3d"] + fl["attn2d"]}
     names = ["gemm", "conv3x3", "attention", "groupnorm", "layernorm", "other"]
     top = max((0, 1, 2), key=lambda k: kind_ms[k])
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:  # noqa: BLE001
-        pass
-    peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
     achieved = alg[top] / (kind_ms[top] * 1e-3) / 1e12
     launches_fwd = unet.forward_launches(2, B, F, h, w)
     launches_step = launches_fwd + 3   # + assemble, cfg-skeleton, cfg+ddim kernels (2 memcpys not counted)
+    traffic, traffic_file = (ncu_traffic() if (world == 1 and names[top] == "attention") else (None, None))
     roofline = {"bound": "tensor", "kernel": names[top], "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": achieved / peak_tf,
-                # dram__bytes_read.sum + dram__bytes_write.sum of the captured attention launch (level-2 3-D layer, grid 1280,
-                # profiles/r01d_ncu_attention.txt); its algorithmic Q/K/V/O bytes are 67.1 MB => no wasted HBM re-reads
-                "traffic": 68148480 if names[top] == "attention" else None,
-                "traffic_note": "ncu --set full capture of one level-2 3-D attention launch: 68.1 MB DRAM vs 67.1 MB algorithmic",
+                "traffic": traffic,
+                "traffic_note": (f"dram__bytes_read.sum + dram__bytes_write.sum of ONE captured launch, parsed at run time from "
+                                 f"{traffic_file} (ncu --set full); not re-measured in this run" if traffic_file else
+                                 "no ncu capture consulted in this run"),
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained",
                 "launches_per_forward": int(n_k[top]), "ms_per_forward": kind_ms[top],
                 "by_kind_ms": {names[k]: round(kind_ms[k], 4) for k in range(6)},
                 "by_kind_tflops": {names[k]: round(alg[k] / (kind_ms[k] * 1e-3) / 1e12, 1) for k in (0, 1, 2)},
+                "by_kind_note": "one UNet forward of the single-GPU W16 plan with the 2F-image pose batch (the window step shares "
+                                "the CFG-negative pose embedding: F+1 images)",
                 "unet_forward_ms_sum": round(sum(kind_ms), 3)}
 
-    jobs = 1 if sharded else world   # sharded: all ranks cooperate on ONE window per step (strong scaling)
-    value = jobs * args.steps / (ms_res * 1e-3)
-    e2e_val = jobs * args.steps / (ms_e2e * 1e-3)
-    h2d = sum(host[k].numel() * host[k].element_size() for k in ("latents", "pixel", "plucker", "skel", "mask", "ts"))
+    value = world * args.steps / (ms_res * 1e-3)
+    e2e_val = world * args.steps / (ms_e2e * 1e-3)
+    h2d = sum(host[k].numel() * host[k].element_size() for k in KEYS)
     d2h = out_host.numel() * 2 + ts_host.numel() * 8
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "strong" if sharded else "weak",
+        "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
         "config": {"workload": wl["name"], "unet": "SD-2.1 layout 320/640/1280/1280, heads 5/10/20/20, in_channels 11 "
                    "(pose encoder + frame-index embedding), no attn2", "images_per_step": B,
-                   "parallelism": (f"frame-sharded window x{world} (fused K/V exchange over NVLink peer memory)" if sharded else
-                                   f"replicas x{world} (independent windows, no collective)" if world > 1 else "single GPU"),
+                   "parallelism": (f"replicas x{world} (independent windows, no collective)" if world > 1 else "single GPU"),
                    "l2": f"no explicit flush: one step streams ~{unet.workspace_bytes(2, B, F, h, w) / 2**30:.1f} GiB of "
                          "activations + 1.6 GB of weights through a 126 MB L2"},
         "tflops_per_step": fl["total"] / 1e12,
-        "unet_tflops_achieved": jobs * fl["total"] / (ms_res / args.steps * 1e-3) / 1e12,
-        "unet_roofline_frac": jobs * fl["total"] / (ms_res / args.steps * 1e-3) / 1e12 / peak_tf / world,
+        "unet_tflops_achieved": fl["total"] / (ms_res / args.steps * 1e-3) / 1e12,
+        "unet_roofline_frac": fl["total"] / (ms_res / args.steps * 1e-3) / 1e12 / peak_tf,
         "roofline": roofline, "clocks": clocks,
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches_step * args.steps,
     }
-    if world == 1 and not args.no_cpu_baseline:
-        times, fl_s, fl_w, threads, smp = cpu_oracle_window_seconds(1, 0, budget_s=25.0)
-        line["cpu_baseline"] = cpu_baseline_obj(times, fl_s, fl_w, threads, smp)
+
+    # ================= N > 1: the same window frame-sharded over all ranks (north-star split) =================
+    if world > 1 and F % world == 0 and not args.no_sharded:
+        from diffuman4d_b200.sharded import FrameShardedPipeline
+        shared = synth_inputs(F, wl["n_cond"], h, w, seed=0)          # every rank: the SAME window
+        # single-GPU result of that window on this rank (bit-identity reference for this rank's frames)
+        step_single, lat_single, ts_single = make_stepper(pipe, shared, wl["domain"])
+        step_single()
+        torch.cuda.synchronize()
+        sh = FrameShardedPipeline(pipe, max_frames=F, h=h, w=w)
+        lo, hi = sh.frames(F)
+        step_sh, lat_sh, ts_sh = make_stepper(pipe, {k: v[lo:hi].contiguous() for k, v in shared.items()}, wl["domain"],
+                                              shard=sh, F_total=F)
+        ssteps = args.steps
+        ms_sh = timed(step_sh, ssteps, 3)
+        same = torch.equal(lat_sh, lat_single[lo:hi]) and torch.equal(ts_sh, ts_single[lo:hi])
+        flag = torch.tensor([1 if same else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        line["sharded"] = {
+            "what": f"ONE W16 window per step, frames split over {world} ranks ({F // world} frames = {2 * F // world} images per rank), "
+                    "K/V of the 11 3-D attention layers exchanged over NVLink peer memory inside the QKV GEMM epilogue",
+            "value": ssteps / (ms_sh * 1e-3), "unit": UNIT, "ms_per_window": ms_sh / ssteps, "scaling": "strong",
+            "speedup_vs_this_runs_single_gpu_step": (ms_res / args.steps) / (ms_sh / ssteps),
+            "bit_identical_to_single_gpu": bool(flag.item()),
+            "unet_roofline_frac_per_gpu": fl["total"] / (ms_sh / ssteps * 1e-3) / 1e12 / peak_tf / world}
+
+    # ================= N = 1 extras: other BASELINE configurations, GPU-eager and CPU baselines =================
+    if world == 1 and not args.quick:
+        also = {}
+        for a in ALSO:
+            try:
+                Fa, ha, wa = a["F"], a["h"], a["w"]
+                pipe.parepare_schedulers(wl["n_steps"], Fa)
+                stp, _, _ = make_stepper(pipe, synth_inputs(Fa, a["n_cond"], ha, wa, seed=1), a["domain"])
+                ms_a = timed(stp, a["steps"], 2)
+                fa = unet_flops(cfg, 2 * Fa, Fa, ha, wa)["total"]
+                also[a["key"]] = {"workload": a["name"], "value": a["steps"] / (ms_a * 1e-3), "unit": UNIT,
+                                  "ms_per_step": ms_a / a["steps"], "steps": a["steps"], "tflops_per_step": fa / 1e12,
+                                  "unet_roofline_frac": fa / (ms_a / a["steps"] * 1e-3) / 1e12 / peak_tf}
+                del stp
+                torch.cuda.empty_cache()
+            except Exception as e:  # noqa: BLE001
+                also[a["key"]] = {"error": str(e)[:200]}
+        line["also"] = also
+        pipe.parepare_schedulers(wl["n_steps"], F)
+        if not args.no_eager_baseline:
+            line["gpu_eager_bf16_baseline"] = gpu_eager_baseline(cfg, sd, full_inputs, dev, args.steps)
+        if not args.no_cpu_baseline:
+            times, threads = cpu_oracle_w16_steps(1, budget_s=30.0)
+            line["cpu_baseline"] = cpu_baseline_obj(times, threads, 1)
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def gpu_eager_baseline(cfg, sd, inputs, dev, steps):
+    """The same window step as the reference would execute it on THIS GPU: the oracle's torch graph in bf16 on
+    cuDNN / cuBLAS / SDPA (eager).  A reported comparator like cpu_baseline -- never part of the product path."""
+    from diffuman4d_b200.config import SchedulerConfig
+    from oracle.pipeline_oracle import DDIMOracle, denoise_window_oracle
+    from oracle.unet_oracle import OracleUNet
+    try:
+        net = OracleUNet(cfg).eval()
+        net.load_state_dict({k: v.float() for k, v in sd.items()})
+        net = net.to(dev).to(torch.bfloat16)
+        sched = DDIMOracle(SchedulerConfig())
+        sched.set_timesteps(WORKLOAD["n_steps"])
+        d = {k: (v.to(torch.bfloat16) if v.dtype.is_floating_point else v).to(dev) for k, v in inputs.items()}
+        sched.timesteps = sched.timesteps.to(dev)
+
+        def unet(x, t, sk, doms, nf):
+            with torch.no_grad():
+                return net(x, t, sk, doms, nf)
+
+        def step():
+            denoise_window_oracle(unet, sched, latents=d["latents"].clone(), pixel_latents=d["pixel"], plucker=d["plucker"],
+                                  skeletons=d["skel"], cond_mask=d["mask"], timestep_indices=d["ts"], domain=WORKLOAD["domain"],
+                                  guidance_scale=WORKLOAD["guidance"])
+        n = max(3, min(steps, 10))
+        for _ in range(2):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n
+        del net
+        torch.cuda.empty_cache()
+        return {"value": 1e3 / ms, "unit": UNIT, "ms_per_step": ms, "steps": n,
+                "what": "oracle torch graph (the reference's graph restated), bf16 eager on this GPU: cuDNN convs, cuBLAS linears, "
+                        "SDPA flash attention, per-frame Python scheduler loop (PIPE:413-423)"}
+    except Exception as e:  # noqa: BLE001
+        return {"error": str(e)[:300]}
 
 
 def main():
@@ -374,8 +491,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--mode", default="replicas", choices=["replicas", "sharded"],
-                    help="N>1: independent windows per GPU (weak) or one frame-sharded window over all GPUs (strong)")
+    ap.add_argument("--no-eager-baseline", action="store_true")
+    ap.add_argument("--no-sharded", action="store_true", help="N>1: skip the frame-sharded `sharded` object")
+    ap.add_argument("--quick", action="store_true", help="N=1: headline only (no `also`, no baselines)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -210,7 +210,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       mbar_wait(&ring_empty[slot], phase ^ 1);
       uint8_t* dst = sRing + slot * C::SLOT_BYTES;
       if (elect_one()) {
-        if (a.dbg & 16) {  // ablation: no K/V traffic
+        if (D4D_DBG(a, 16)) {  // ablation: no K/V traffic
           mbar_arrive(&ring_full[slot]);
         } else {
           mbar_expect_tx(&ring_full[slot], C::SLOT_BYTES);
@@ -255,7 +255,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         for (int k = 0; k < 4; ++k) {
           const uint64_t ad = make_smem_desc(q_addr + nb * QTILE_BYTES + k * 32, 0, 1024, 2);
           const uint64_t bd = make_smem_desc(kaddr + nb * KTILE_BYTES + k * 32, 0, 1024, 2);
-          if (!(a.dbg & 8)) umma_ss(s_tmem, ad, bd, idesc_qk, (nb | k) != 0 ? 1u : 0u);
+          if (!D4D_DBG(a, 8)) umma_ss(s_tmem, ad, bd, idesc_qk, (nb | k) != 0 ? 1u : 0u);
         }
       }
     };
@@ -267,7 +267,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         // V tile = NB boxes of [64 keys][64 d] (d contiguous): MN-major B operand.
         // 16 keys = two 8-row swizzle atoms = 2048 bytes; SBO = 1024 (next 8 keys), LBO = next 64-wide d block
         const uint64_t bd = make_smem_desc(vaddr + k * 2048, KTILE_BYTES, 1024, 2);
-        if (!(a.dbg & 4)) umma_ts(o_tmem, p_tmem + k * 8, bd, idesc_pv, (j | k) != 0 ? 1u : 0u);
+        if (!D4D_DBG(a, 4)) umma_ts(o_tmem, p_tmem + k * 8, bd, idesc_pv, (j | k) != 0 ? 1u : 0u);
       }
     };
     auto advance = [&]() {
@@ -356,7 +356,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       const bool next_ready = (j + 1 < n_tiles) && __all_sync(0xffffffffu, mbar_test(&s_full[buf ^ 1], ((j + 1) >> 1) & 1));
 
       float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-      if (a.dbg & 64) {  // ablation: barriers only
+      if (D4D_DBG(a, 64)) {  // ablation: barriers only
         tc_fence_before();
         pready_arrive(buf);
         if (j + 1 < n_tiles) {
@@ -380,7 +380,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       uint64_t lsum[2] = {0ull, 0ull};
       if (j > 0) {  // speculative P with the running max of the previous tiles
         const uint64_t nm2 = pack2(-m, -m);
-        if (full) { exp32<false>(sv, sc2, nm2, lsum, p_tmem, 32, a.dbg); exp32<false>(sv + 32, sc2, nm2, lsum, p_tmem + 16, 32, a.dbg); }
+        if (full) { exp32<false>(sv, sc2, nm2, lsum, p_tmem, 32, D4D_DBGV(a)); exp32<false>(sv + 32, sc2, nm2, lsum, p_tmem + 16, 32, D4D_DBGV(a)); }
         else { exp32<true>(sv, sc2, nm2, lsum, p_tmem, valid); exp32<true>(sv + 32, sc2, nm2, lsum, p_tmem + 16, valid - 32); }
       }
       const bool ovf = !(tmax <= m + 100.f);  // would overflow with the old max; always true for tile 0 (m = -inf)
@@ -400,7 +400,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         const uint64_t nm2 = pack2(-m, -m);
         lsum[0] = 0ull;
         lsum[1] = 0ull;
-        if (full) { exp32<false>(sv, sc2, nm2, lsum, p_tmem, 32, a.dbg); exp32<false>(sv + 32, sc2, nm2, lsum, p_tmem + 16, 32, a.dbg); }
+        if (full) { exp32<false>(sv, sc2, nm2, lsum, p_tmem, 32, D4D_DBGV(a)); exp32<false>(sv + 32, sc2, nm2, lsum, p_tmem + 16, 32, D4D_DBGV(a)); }
         else { exp32<true>(sv, sc2, nm2, lsum, p_tmem, valid); exp32<true>(sv + 32, sc2, nm2, lsum, p_tmem + 16, valid - 32); }
       } else if (tmax > m + 8.f) {
         // lazy rescale: this tile used the old max; fold the change into O and l before the next tile
@@ -420,7 +420,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         if (!next_ready) mbar_wait(&s_full[buf ^ 1], ((j + 1) >> 1) & 1);
         tc_fence_after();
         const uint32_t s_next = tmem + C::COL_S + (buf ^ 1) * 64 + lane_sel;
-        if (!(a.dbg & 32)) {
+        if (!D4D_DBG(a, 32)) {
           tmem_ld32(s_next, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
           tmem_ld32(s_next + 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[32]));
         }
@@ -465,8 +465,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 template <int NB>
 int launch_attn(const AttnLaunch& L, cudaStream_t stream) {
   using C = AttCfg<NB>;
-  static bool attr_set[64] = {};
-  if (int rc = ensure_dyn_smem(attn_fwd_kernel<NB>, C::SMEM_BYTES, attr_set)) return rc;
+  static PerDeviceOnce attr_once;
+  if (int rc = ensure_dyn_smem(attn_fwd_kernel<NB>, C::SMEM_BYTES, attr_once)) return rc;
   AttKernelArgs a;
   a.seq_q = L.d.seq;
   a.seq_kv = L.d.seq_kv > 0 ? L.d.seq_kv : L.d.seq;
@@ -475,14 +475,10 @@ int launch_attn(const AttnLaunch& L, cudaStream_t stream) {
   a.scale_log2 = L.d.scale * 1.4426950408889634f;
   a.out = L.d.out;
   a.ld_out = L.d.ld_out;
-  {
-    static int dbg = -1;
-    if (dbg < 0) {
-      const char* e = getenv("D4D_ATTN_ABLATE");
-      dbg = e ? atoi(e) : 0;
-    }
-    a.dbg = dbg;
-  }
+  a.dbg = 0;
+#ifdef D4D_ABLATE
+  a.dbg = ablate_env("D4D_ATTN_ABLATE");
+#endif
   dim3 grid(L.grid_x, L.grid_y);
   D4D_CUDA_OK(launch_pdl(attn_fwd_kernel<NB>, grid, dim3(ATT_THREADS), C::SMEM_BYTES, stream, L.tmap_q, L.tmap_k, L.tmap_v, a));
   D4D_CUDA_OK(cudaGetLastError());

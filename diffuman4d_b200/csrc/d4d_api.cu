@@ -297,6 +297,19 @@ int d4d_op_layernorm(const void* x, int rows, int C, float eps, const float* gam
   D4D_API_END
 }
 
+int d4d_debug_tap(d4d_handle* h, const void* sample, const int64_t* timestep, const void* skeletons,
+                  const int32_t* domain_ids, int n_domains, int B, int F, int height, int width, int tap, void* out,
+                  char* name64, int32_t* dims3, void* stream) {
+  D4D_API_BEGIN
+  D4D_REQUIRE(h != nullptr, "null handle");
+  DeviceGuard g(h->model->device());
+  return h->model->debug_tap(static_cast<const bf16*>(sample), reinterpret_cast<const long long*>(timestep),
+                             static_cast<const bf16*>(skeletons), domain_ids, n_domains, B, F, height, width, tap,
+                             static_cast<bf16*>(out), name64, dims3, static_cast<cudaStream_t>(stream));
+  D4D_API_END
+}
+
+#ifdef D4D_TEST_KERNELS  // libd4d_test.so only (include/d4d_test.h)
 int d4d_op_probe_umma(const void* A, const void* B, float* D, int N, int K, int a_src, int b_major, uint32_t b_lbo,
                       uint32_t b_sbo, uint32_t b_kadv, void* stream) {
   D4D_API_BEGIN
@@ -311,6 +324,8 @@ int d4d_microbench(int kind, int warps, int iters, int blocks, uint64_t* cycles_
                              static_cast<cudaStream_t>(stream));
   D4D_API_END
 }
+
+#endif  // D4D_TEST_KERNELS
 
 int d4d_unet_forward_sharded(d4d_handle* h, const void* sample, const int64_t* timestep, const void* skeletons,
                              const int32_t* domain_ids, int n_domains, int B_local, int F_local, int F_total, int height,

@@ -142,7 +142,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         mbar_wait(&empty[stage], phase ^ 1);
         uint8_t* sa = smem + stage * STAGE_BYTES;
         uint8_t* sb = sa + A_BYTES;
-        if (a.dbg & 1) {  // ablation: no loads (D4D_GEMM_ABLATE)
+        if (D4D_DBG(a, 1)) {  // ablation: no loads (tools build only)
           if (elect_one()) mbar_arrive(&full[stage]);
         } else if (a.mode == 0) {
           const bool first = kb < a.kb_split;
@@ -193,7 +193,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           ready = __all_sync(0xffffffffu, mbar_test(&full[ns], np));
         }
         if (elect_one()) {
-          if (!(a.dbg & 2)) {
+          if (!D4D_DBG(a, 2)) {
 #pragma unroll
             for (int k = 0; k < BLOCK_K / 16; ++k) {
               // advancing 16 bf16 along K inside the 128B swizzle atom = +32 bytes = +2 in the (addr>>4) field
@@ -276,7 +276,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(t[i].x), "=r"(t[i].y), "=r"(t[i].z), "=r"(t[i].w) : "r"(addr) : "memory");
         }
         __syncwarp();  // the next unit may overwrite the staging rows
-        if (t_piece < pieces && !(a.dbg & 32)) {
+        if (t_piece < pieces && !D4D_DBG(a, 32)) {
 #pragma unroll
           for (int i = 0; i < 4; ++i)
             if (t_valid[i]) *reinterpret_cast<uint4*>(a.out + static_cast<size_t>(t_row[i]) * a.ldo + ocol + t_piece * 8) = t[i];
@@ -296,7 +296,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         uint4 r0 = z4, r1 = z4, v0 = z4, v1 = z4, nr0 = z4, nr1 = z4, nv0 = z4, nv1 = z4;
         const bf16* res_row = a.residual ? a.residual + static_cast<size_t>(row) * a.ld_res + n0 : nullptr;
         const bf16* rv_row = a.rowvec ? a.rowvec + static_cast<size_t>(img) * a.ld_rowvec + n0 : nullptr;
-        const bool ld_res = valid && res_row != nullptr && !(a.dbg & 64), ld_rv = valid && rv_row != nullptr;
+        const bool ld_res = valid && res_row != nullptr && !D4D_DBG(a, 64), ld_rv = valid && rv_row != nullptr;
         if (chunk_at(0) < chunks) {
           const int c0 = chunk_at(0);
           if (ld_res) {  // plain loads: the residual may alias the output (in-place add)
@@ -422,7 +422,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             o1.x = pack_bf16x2(o[8], o[9]);   o1.y = pack_bf16x2(o[10], o[11]);
             o1.z = pack_bf16x2(o[12], o[13]); o1.w = pack_bf16x2(o[14], o[15]);
             // direct row-wise stores: this epilogue is bound by the GEGLU math, staging only adds to it (measured)
-            if (!(a.dbg & 32)) {
+            if (!D4D_DBG(a, 32)) {
               uint4* op = reinterpret_cast<uint4*>(a.out + static_cast<size_t>(row) * a.ldo + n_tile * half + c * 16);
               op[0] = o0;
               op[1] = o1;
@@ -473,14 +473,9 @@ int gemm_prepare(const GemmDesc& d, GemmLaunch* L) {
   }
   D4D_REQUIRE(bn >= 16 && d.N % bn == 0 && bn % (d.geglu ? 32 : 16) == 0, "no valid block_n");
   a.block_n = bn;
-  {
-    static int dbg = -1;
-    if (dbg < 0) {
-      const char* e = getenv("D4D_GEMM_ABLATE");
-      dbg = e ? atoi(e) : 0;
-    }
-    a.dbg = dbg;
-  }
+#ifdef D4D_ABLATE
+  a.dbg = ablate_env("D4D_GEMM_ABLATE");
+#endif
   a.n_tiles = d.N / bn;
   a.N = d.N;
   a.bias = d.bias;
@@ -554,12 +549,12 @@ int gemm_prepare(const GemmDesc& d, GemmLaunch* L) {
 }
 
 int gemm_run(const GemmLaunch& L, cudaStream_t stream) {
-  static bool attr_set[2][64] = {};
+  static PerDeviceOnce attr_once[2];
   if (L.args.geglu) {
-    if (int rc = ensure_dyn_smem(gemm_umma_kernel<true>, SMEM_BYTES, attr_set[1])) return rc;
+    if (int rc = ensure_dyn_smem(gemm_umma_kernel<true>, SMEM_BYTES, attr_once[1])) return rc;
     D4D_CUDA_OK(launch_pdl(gemm_umma_kernel<true>, dim3(L.grid), dim3(NUM_THREADS), SMEM_BYTES, stream, L.tmap_a, L.tmap_a2, L.tmap_b, L.args));
   } else {
-    if (int rc = ensure_dyn_smem(gemm_umma_kernel<false>, SMEM_BYTES, attr_set[0])) return rc;
+    if (int rc = ensure_dyn_smem(gemm_umma_kernel<false>, SMEM_BYTES, attr_once[0])) return rc;
     D4D_CUDA_OK(launch_pdl(gemm_umma_kernel<false>, dim3(L.grid), dim3(NUM_THREADS), SMEM_BYTES, stream, L.tmap_a, L.tmap_a2, L.tmap_b, L.args));
   }
   D4D_CUDA_OK(cudaGetLastError());

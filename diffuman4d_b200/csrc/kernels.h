@@ -2,6 +2,7 @@
 // executor (unet.cu).  Every launcher returns 0 on success, non-zero after d4d::set_error().
 #pragma once
 #include <cstdlib>
+#include <mutex>
 #include <utility>
 #include <string.h>
 
@@ -189,23 +190,42 @@ struct KvFlagArgs {
 int kv_signal_run(const KvFlagArgs& a, cudaStream_t stream);
 int kv_wait_run(const KvFlagArgs& a, cudaStream_t stream);
 
+#ifdef D4D_TEST_KERNELS  // measurement / probe kernels: only in libd4d_test.so (build.py), never in the product library
 // device microbenchmarks (microbench.cu)
 int microbench_run(int kind, int warps, int iters, int blocks, unsigned long long* cycles_dev, float* sink_dev, cudaStream_t s);
 
 // UMMA operand-encoding probe (probe.cu)
 int probe_umma_run(const bf16* A, const bf16* B, float* D, int N, int K, int a_src, int b_major, uint32_t b_lbo,
                    uint32_t b_sbo, uint32_t b_kadv, cudaStream_t stream);
+#endif
 
-// per-device "opt in to large dynamic smem" helper
+// Ablation switches (tools/ablate_*.py) exist only in the tools build (-DD4D_ABLATE, libd4d_test.so); in the product
+// library the tests below are compile-time false and no environment variable is read.
+#ifdef D4D_ABLATE
+#define D4D_DBG(args, bit) (((args).dbg & (bit)) != 0)
+#define D4D_DBGV(args) ((args).dbg)
+inline int ablate_env(const char* name) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : 0;
+}
+#else
+#define D4D_DBG(args, bit) false
+#define D4D_DBGV(args) 0
+#endif
+
+// per-device "opt in to large dynamic smem" helper.  `once` holds one flag per device ordinal; the reference drives one
+// pipeline per GPU from its own thread (sampling_runner.py:36-43), so the first launches may race: std::call_once.
+struct PerDeviceOnce {
+  std::once_flag flag[64];
+};
 template <typename F>
-inline int ensure_dyn_smem(F func, int bytes, bool* done_per_device) {
+inline int ensure_dyn_smem(F func, int bytes, PerDeviceOnce& once) {
   int dev = 0;
   D4D_CUDA_OK(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 64) return 0;
-  if (!done_per_device[dev]) {
-    D4D_CUDA_OK(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    done_per_device[dev] = true;
-  }
+  cudaError_t err = cudaSuccess;
+  std::call_once(once.flag[dev], [&] { err = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); });
+  D4D_CUDA_OK(err);
   return 0;
 }
 
@@ -213,12 +233,11 @@ inline int ensure_dyn_smem(F func, int bytes, bool* done_per_device) {
 // execute pdl_wait() (common.cuh) before touching anything a predecessor wrote.  Measured on the W16 step: 46.63 ms with the
 // attribute vs 46.55 ms without (the kernels are long enough that launch gaps do not show), so it is opt-in: D4D_PDL=1.
 inline bool pdl_enabled() {
-  static int on = -1;
-  if (on < 0) {
+  static const bool on = [] {
     const char* e = getenv("D4D_PDL");
-    on = (e && e[0] == '1') ? 1 : 0;
-  }
-  return on == 1;
+    return e && e[0] == '1';
+  }();  // thread-safe one-time initialisation
+  return on;
 }
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {

@@ -134,9 +134,9 @@ int probe_umma_run(const bf16* A, const bf16* B, float* D, int N, int K, int a_s
   p.N = N; p.K = K; p.a_src = a_src; p.b_major = b_major;
   p.b_lbo = b_lbo; p.b_sbo = b_sbo; p.b_kadv = b_kadv;
   p.A = A; p.D = D;
-  static bool attr_set[64] = {};
+  static PerDeviceOnce attr_once;
   const int smem = 65536 + 1024 + 64;
-  if (int rc = ensure_dyn_smem(probe_kernel, smem, attr_set)) return rc;
+  if (int rc = ensure_dyn_smem(probe_kernel, smem, attr_once)) return rc;
   probe_kernel<<<1, 128, smem, stream>>>(ta, tb, p);
   D4D_CUDA_OK(cudaGetLastError());
   return 0;

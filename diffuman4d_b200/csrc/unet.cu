@@ -88,8 +88,8 @@ Model::~Model() {
   for (void* p : dev_allocs_) cudaFree(p);
 }
 
-void Model::need(const std::string& key, int64_t numel) {
-  expected_[key] = numel;
+void Model::need(const std::string& key, std::vector<int64_t> shape) {
+  expected_[key] = std::move(shape);
   key_order_.push_back(key);
 }
 
@@ -97,16 +97,16 @@ void Model::declare_keys() {
   const int* ch = cfg_.block_out_channels;
   const int C0 = ch[0], TE = 4 * C0, L = cfg_.layers_per_block;
   auto lin = [&](const std::string& p, int out, int in, bool bias = true) {
-    need(p + ".weight", static_cast<int64_t>(out) * in);
-    if (bias) need(p + ".bias", out);
+    need(p + ".weight", {out, in});
+    if (bias) need(p + ".bias", {out});
   };
   auto conv = [&](const std::string& p, int out, int in, int k) {
-    need(p + ".weight", static_cast<int64_t>(out) * in * k * k);
-    need(p + ".bias", out);
+    need(p + ".weight", {out, in, k, k});
+    need(p + ".bias", {out});
   };
   auto norm = [&](const std::string& p, int c) {
-    need(p + ".weight", c);
-    need(p + ".bias", c);
+    need(p + ".weight", {c});
+    need(p + ".bias", {c});
   };
   auto resnet = [&](const std::string& p, int cin, int cout) {
     norm(p + ".norm1", cin);
@@ -148,7 +148,7 @@ void Model::declare_keys() {
     static const int spec[8][3] = {{3, 3, 3}, {3, 16, 4}, {16, 16, 3}, {16, 32, 4}, {32, 32, 3}, {32, 64, 4}, {64, 64, 3}, {64, 128, 3}};
     for (int i = 0; i < 8; ++i) conv("pose_encoder.conv_layers." + std::to_string(2 * i), spec[i][1], spec[i][0], spec[i][2]);
     conv("pose_encoder.final_proj", C0, 128, 1);
-    need("pose_encoder.scale", 1);
+    need("pose_encoder.scale", {1});
   }
   int cout = C0;
   for (int i = 0; i < 4; ++i) {
@@ -190,13 +190,24 @@ int Model::load_weight(const char* key, const void* data, const int64_t* shape, 
     set_error(std::string("unknown weight key: ") + key);
     return 1;
   }
-  int64_t numel = 1;
-  for (int i = 0; i < ndim; ++i) numel *= shape[i];
-  if (numel != it->second) {
-    set_error(std::string("shape mismatch for ") + key + ": got " + std::to_string(numel) + " elements, expected " +
-              std::to_string(it->second));
+  // full shape check (a transposed / mis-shaped tensor with the right element count must not load silently); trailing
+  // dims of size 1 are ignored so that 1x1-conv [C, C, 1, 1] and Linear [C, C] projections are interchangeable
+  auto squeeze = [](std::vector<int64_t> v) {
+    while (v.size() > 1 && v.back() == 1) v.pop_back();
+    return v;
+  };
+  const std::vector<int64_t> got = squeeze(std::vector<int64_t>(shape, shape + ndim)), want = squeeze(it->second);
+  auto fmt = [](const std::vector<int64_t>& v) {
+    std::string o = "[";
+    for (size_t i = 0; i < v.size(); ++i) o += (i ? ", " : "") + std::to_string(v[i]);
+    return o + "]";
+  };
+  if (got != want) {
+    set_error(std::string("shape mismatch for ") + key + ": got " + fmt(got) + ", expected " + fmt(want));
     return 1;
   }
+  int64_t numel = 1;
+  for (int i = 0; i < ndim; ++i) numel *= shape[i];
   HostTensor& t = staged_[key];
   t.shape.assign(shape, shape + ndim);
   t.v.resize(static_cast<size_t>(numel));
@@ -518,6 +529,9 @@ class PlanBuilder {
       p_.op_kind.push_back(kind);
       p_.op_flops.push_back(flops);
     }
+  }
+  void tap(const std::string& name, const Act& a) {
+    if (!dry_) p_.taps.push_back({name, a.p, a.C, a.H, a.W, p_.ops.size()});
   }
   void gemm(const GemmDesc& d) {
     if (dry_) { p_.launches += 1; return; }
@@ -874,6 +888,7 @@ class PlanBuilder {
       if (pose_emb) release(pose_emb);
       x = {x0, C0, h, w};
     }
+    tap("conv_in", x);
 
     // ---- 3. down: UNET:557-565 ----
     std::vector<Act> skips;
@@ -903,6 +918,7 @@ class PlanBuilder {
         x = {y, x.C, Ho, Wo};
         skips.push_back(x);
       }
+      tap("down_blocks." + std::to_string(i), x);
     }
     // ---- 4. mid: UNET:568-572 ----
     {
@@ -913,6 +929,7 @@ class PlanBuilder {
       release(z.p);
       x = u;
     }
+    tap("mid_block", x);
     // ---- 5. up: UNET:575-587 ----
     for (int i = 0; i < 4; ++i) {
       const int nf = i < cfg.num_3d_attn_blocks ? F : 1;
@@ -939,6 +956,7 @@ class PlanBuilder {
         release(up);
         x = y;
       }
+      tap("up_blocks." + std::to_string(i), x);
     }
     // ---- 6. out: UNET:590-593 ----
     {
@@ -1045,6 +1063,31 @@ int Model::forward(const bf16* sample, const long long* timestep, const bf16* sk
   p->run_index++;
   xch_.epoch_base += static_cast<unsigned int>(p->n3d);
   return 0;
+}
+
+int Model::debug_tap(const bf16* sample, const long long* timestep, const bf16* skeletons, const int* domain_ids, int n_domains,
+                     int B, int F, int h, int w, int tap, bf16* out, char* name64, int* dims3, cudaStream_t stream) {
+  D4D_REQUIRE(domain_ids != nullptr, "null argument");
+  Plan* p = nullptr;
+  if (int rc = get_plan(domain_ids, n_domains, B, F, h, w, &p)) return rc;
+  if (tap < 0 || tap >= static_cast<int>(p->taps.size())) {
+    set_error("tap index out of range");
+    return 1;
+  }
+  const Plan::Tap& t = p->taps[tap];
+  if (name64) {
+    strncpy(name64, t.name.c_str(), 63);
+    name64[63] = 0;
+  }
+  if (dims3) { dims3[0] = t.C; dims3[1] = t.H; dims3[2] = t.W; }
+  if (!out) return 0;
+  D4D_REQUIRE(sample && timestep, "null argument");
+  D4D_REQUIRE(!cfg_.enable_pose_encoder || skeletons != nullptr, "skeletons are required when enable_pose_encoder");
+  D4D_CUDA_OK(cudaSetDevice(device_));
+  p->sample = sample; p->timestep = timestep; p->skeletons = skeletons; p->out = nullptr;
+  for (size_t i = 0; i < t.n_ops; ++i)
+    if (int rc = p->ops[i](stream)) return rc;
+  return nhwc_to_nchw_run(t.p, t.C, B, t.C, t.H * t.W, out, stream);
 }
 
 int Model::exchange_alloc(size_t kv_bytes, unsigned char* handles_out) {

@@ -55,6 +55,10 @@ struct Plan {
   std::vector<int> op_kind;       // 0 gemm, 1 conv3x3, 2 attention, 3 groupnorm, 4 layernorm, 5 other
   std::vector<double> op_flops;   // executed FLOPs (incl. tile/head padding) of tensor-core ops
   std::vector<cudaEvent_t> events; // lazily created by profile()
+  // debug taps (per-level drift report, tests/test_gpu_fullsize.py): a named intermediate activation [B*H*W, C] (NHWC) that is
+  // complete once ops[0 .. n_ops) have run; the arena may reuse its storage afterwards
+  struct Tap { std::string name; const bf16* p; int C, H, W; size_t n_ops; };
+  std::vector<Tap> taps;
   // per-call externals, set by Model::forward before running the ops
   const bf16* sample = nullptr;
   const long long* timestep = nullptr;
@@ -105,6 +109,10 @@ class Model {
               double* flops_by_kind);
   int get_plan(const int* domain_ids, int n_domains, int B, int F, int h, int w, Plan** out, int F_total = 0,
                bool pose_shared_neg = false);
+  // debug: run the forward up to tap `tap` and copy that activation out as NCHW bf16 [B, C, H, W]; out == nullptr only
+  // reports name / dims.  Returns 1 when tap is out of range.
+  int debug_tap(const bf16* sample, const long long* timestep, const bf16* skeletons, const int* domain_ids, int n_domains,
+                int B, int F, int h, int w, int tap, bf16* out, char* name64, int* dims3, cudaStream_t stream);
   Plan* find_plan(int n_domains, int B, int F, int h, int w);
   const std::vector<std::string>& keys() const { return key_order_; }
   int device() const { return device_; }
@@ -114,7 +122,7 @@ class Model {
   d4d_config cfg_;
   int device_;
   bool finalized_ = false;
-  std::map<std::string, int64_t> expected_;  // key -> numel
+  std::map<std::string, std::vector<int64_t>> expected_;  // key -> diffusers shape (trailing 1s dropped)
   std::vector<std::string> key_order_;
   std::map<std::string, HostTensor> staged_;
   std::vector<void*> dev_allocs_;
@@ -137,7 +145,7 @@ class Model {
   std::map<std::string, std::unique_ptr<WindowBufs>> wbufs_;
   Exchange xch_;
 
-  void need(const std::string& key, int64_t numel);
+  void need(const std::string& key, std::vector<int64_t> shape);
   void declare_keys();
   int cin_pad() const { return 16; }
   int kp_in() const { return 192; }

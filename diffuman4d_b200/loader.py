@@ -10,9 +10,11 @@ snapshot download of the reference is mirrored, otherwise the directory must alr
 """
 from __future__ import annotations
 
+import importlib
 import json
 import os
-from typing import List, Optional
+import warnings
+from typing import Callable, List, Optional, Union
 
 import torch
 
@@ -73,9 +75,62 @@ def scheduler_config_from_json(d: dict) -> SchedulerConfig:
         clip_sample=d.get("clip_sample", True), clip_sample_range=d.get("clip_sample_range", 1.0))
 
 
+class StockVAEAdapter:
+    """``encode_latents`` / ``decode_latents`` over a stock diffusers ``AutoencoderKL`` with the reference's exact
+    semantics: ``encode_vae`` / ``decode_vae`` (PIPE:47-72: batches of 8, ``latent_dist.sample() * scaling_factor``,
+    ``decode(z / scaling_factor)``) and the ``output_type="pt"`` post-processing of ``post_process`` (PIPE:280-285:
+    ``(x / 2 + 0.5).clamp(0, 1)``).  The VAE is SURVEY.md section 8f row 1 ("next"), not part of the CUDA hot path."""
+
+    def __init__(self, vae, batch_size: int = 8):
+        self.vae, self.batch_size = vae, batch_size
+
+    def encode_latents(self, images):
+        out = [self.vae.encode(x).latent_dist.sample() for x in images.split(self.batch_size)]
+        return torch.cat(out, dim=0) * self.vae.config.scaling_factor
+
+    def decode_latents(self, latents):
+        sf = self.vae.config.scaling_factor
+        out = [self.vae.decode(z / sf, return_dict=False)[0] for z in latents.split(self.batch_size)]
+        return (torch.cat(out, dim=0) / 2 + 0.5).clamp(0, 1)
+
+
+def default_vae_factory(model_dir: str, gpu_id: int):
+    """Stock ``AutoencoderKL`` from ``model_dir/vae`` (what ``Diffuman4DPipeline.from_pretrained`` loads, SUTIL:45-47).
+    Returns None (with a warning) when the checkpoint has no ``vae/`` or diffusers is not importable: the pipeline then
+    accepts latents only and raises "no VAE attached" for image inputs."""
+    if not os.path.isdir(os.path.join(model_dir, "vae")):
+        return None
+    try:
+        from diffusers import AutoencoderKL
+    except Exception as e:  # noqa: BLE001
+        warnings.warn(f"{model_dir}/vae exists but diffusers is not importable ({e}); pipelines accept latents only")
+        return None
+    vae = AutoencoderKL.from_pretrained(os.path.join(model_dir, "vae"), torch_dtype=torch.bfloat16).to(f"cuda:{gpu_id}")
+    return StockVAEAdapter(vae.eval())
+
+
+def _resolve_factory(vae_factory: Union[None, str, Callable]) -> Callable:
+    """``vae_factory``: None (default above), a callable ``(model_dir, gpu_id) -> vae`` or -- so that a Hydra yaml can
+    name it -- a dotted path ``"package.module.function"`` to such a callable.  The returned ``vae`` object must offer
+    ``encode_latents(images)`` and ``decode_latents(latents)``."""
+    if vae_factory is None:
+        return default_vae_factory
+    if isinstance(vae_factory, str):
+        mod, _, attr = vae_factory.rpartition(".")
+        if not mod:
+            raise ValueError(f"vae_factory must be a dotted path 'module.function', got {vae_factory!r}")
+        vae_factory = getattr(importlib.import_module(mod), attr)
+    if not callable(vae_factory):
+        raise ValueError("vae_factory must be None, a dotted path or a callable (model_dir, gpu_id) -> vae")
+    return vae_factory
+
+
 def load_pipelines(repo_id: str = "krahets/Diffuman4D", model_dir: str = "./models/krahets-Diffuman4D",
-                   torch_dtype: str = "bf16", gpu_ids: Optional[List[int]] = None, vae_factory=None):
-    """Same signature as the reference factory; returns one ``B200Diffuman4DPipeline`` per GPU."""
+                   torch_dtype: str = "bf16", gpu_ids: Optional[List[int]] = None,
+                   vae_factory: Union[None, str, Callable] = None):
+    """Same signature as the reference factory (+ ``vae_factory``, see ``_resolve_factory``); returns one
+    ``B200Diffuman4DPipeline`` per GPU."""
+    make_vae = _resolve_factory(vae_factory)
     if torch_dtype != "bf16":
         raise ValueError(f"Unsupported torch_dtype: {torch_dtype}. The B200 path supports 'bf16' only.")
     if gpu_ids is None:
@@ -95,6 +150,6 @@ def load_pipelines(repo_id: str = "krahets/Diffuman4D", model_dir: str = "./mode
     pipelines = []
     for gpu_id in gpu_ids:
         unet = B200MultiviewUNet(ucfg, device=gpu_id).load_state_dict(sd)
-        vae = vae_factory(model_dir, gpu_id) if vae_factory is not None else None
+        vae = make_vae(model_dir, gpu_id)
         pipelines.append(B200Diffuman4DPipeline(unet, scfg, vae=vae))
     return pipelines

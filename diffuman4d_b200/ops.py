@@ -6,7 +6,7 @@ from typing import Optional
 
 import torch
 
-from ._lib import check, lib
+from ._lib import check, lib, test_lib
 
 
 def _p(t: Optional[torch.Tensor]):
@@ -121,7 +121,8 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
 
 def probe_umma(A: torch.Tensor, B: torch.Tensor, N: int, K: int, a_src: int, b_major: int, b_lbo: int, b_sbo: int,
                b_kadv: int) -> torch.Tensor:
+    """UMMA operand-encoding probe: lives in the tools build libd4d_test.so, not in the product library."""
     D = torch.empty(128, N, device=A.device, dtype=torch.float32)
-    check(lib().d4d_op_probe_umma(_p(A), _p(B), _p(D), N, K, a_src, b_major, b_lbo, b_sbo, b_kadv, _stream()),
+    check(test_lib().d4d_op_probe_umma(_p(A), _p(B), _p(D), N, K, a_src, b_major, b_lbo, b_sbo, b_kadv, _stream()),
           "d4d_op_probe_umma")
     return D

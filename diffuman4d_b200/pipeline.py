@@ -125,6 +125,9 @@ class B200Diffuman4DPipeline:
         if schedulers is None:
             self.parepare_schedulers(num_inference_steps, F_)
             timestep_indices = torch.zeros(F_)
+        if latents is None:        # PIPE:172-183 prepare_latents: draw the initial noise
+            latents = torch.randn(tuple(pixel_values_latents.shape), generator=unused.get("generator"), device=self.device,
+                                  dtype=torch.bfloat16)
         lat = (latents * self.scheduler.init_noise_sigma).to(device=self.device, dtype=torch.bfloat16).contiguous().clone()
         ti = timestep_indices.to(device=self.device, dtype=torch.int64).contiguous().clone()
         self.denoise_window(latents=lat, pixel_values_latents=pixel_values_latents,
@@ -165,23 +168,26 @@ class B200Diffuman4DPipeline:
             raise ValueError(
                 f"The timestep indices should be 0 for all input samples, timestep_indices = {timestep_indices}")
 
-        # ---- latent preparation (PIPE:193-263).  VAE = pluggable, everything else is resizing ----
+        # ---- latent preparation (PIPE:193-263: prepare_all_latents).  Resizes run in the SOURCE dtype and are cast
+        # afterwards, like the reference's encode_image_resizing (PIPE:90-100) ----
         if pixel_values_latents is None:
             if self.vae is None:
                 raise ValueError("no VAE attached: pass pixel_values_latents (and skeletons_latents) instead of images")
             pixel_values_latents = self.vae.encode_latents(pixel_values.to(dev, torch.bfloat16))
         pixel_values_latents = pixel_values_latents.to(dev, torch.bfloat16)
         n, _, h, w = pixel_values_latents.shape
-        plk = plucker_embeds.to(dev, torch.bfloat16)
+        plk = plucker_embeds.to(dev)
         if plk.shape[-2:] != (h, w):
-            plk = torch.nn.functional.interpolate(plk.float(), size=(h, w), mode="bilinear").to(torch.bfloat16)
-        msk = cond_masks.to(dev, torch.bfloat16)
+            plk = torch.nn.functional.interpolate(plk, size=(h, w), mode="bilinear")
+        plk = plk.to(torch.bfloat16)
+        msk = cond_masks.to(dev)
         if msk.shape[-2:] != (h, w):
-            msk = torch.nn.functional.interpolate(msk.float(), size=(h, w), mode="nearest").to(torch.bfloat16)
-        if self.unet.config.enable_pose_encoder:
-            skl = skeletons.to(dev, torch.bfloat16)
-        elif skeletons_latents is not None:
+            msk = torch.nn.functional.interpolate(msk, size=(h, w), mode="nearest")
+        msk = msk.to(torch.bfloat16)
+        if skeletons_latents is not None:                      # same precedence as PIPE:228-241
             skl = skeletons_latents.to(dev, torch.bfloat16)
+        elif self.unet.config.enable_pose_encoder:
+            skl = skeletons.to(dev, torch.bfloat16)
         else:
             if self.vae is None:
                 raise ValueError("no VAE attached: pass skeletons_latents")

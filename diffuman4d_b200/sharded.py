@@ -54,10 +54,42 @@ class FrameShardedPipeline:
     def frames(self, F_total: int):
         return frame_shard(F_total, self.rank, self.world)
 
+    def _bf16(self, t, name):
+        """Same argument contract as the single-GPU path (pipeline.py ``denoise_window``): raw pointers cross the C ABI, so a
+        CPU / strided / wrongly typed tensor must be rejected here instead of surfacing as a peer K/V-flag timeout."""
+        if t is None:
+            raise ValueError(f"{name} is required")
+        t = t.to(device=self.pipe.device, dtype=torch.bfloat16)
+        return t if t.is_contiguous() else t.contiguous()
+
+    @staticmethod
+    def _inplace(t, name, dtype):
+        if not (torch.is_tensor(t) and t.is_cuda and t.dtype == dtype and t.is_contiguous()):
+            raise ValueError(f"{name} must be a contiguous CUDA {str(dtype).replace('torch.', '')} tensor (updated in place)")
+
     def unet_forward(self, sample, timestep, skeletons, domains: List[str], F_local: int, F_total: int):
         """B-2 on this rank's frames: sample [len(domains)*F_local, Cin, h, w] (CFG-major like the reference batch)."""
         unet = self.pipe.unet
+        sample = self._bf16(sample, "sample")
+        if sample.dim() != 4 or sample.shape[1] != unet.config.in_channels:
+            raise ValueError(f"sample must be [B, {unet.config.in_channels}, h, w]")
         B, _, H, W = sample.shape
+        if len(domains) * F_local != B:
+            raise ValueError(f"num_frames: {F_local} * len(domains): {len(domains)} != len(emb): {B}")
+        if F_local * self.world != F_total:
+            raise ValueError(f"F_total ({F_total}) must equal world ({self.world}) * local frames ({F_local})")
+        for d in domains:
+            if d not in _DOMAIN_IDS:
+                raise ValueError(f"Invalid domain for temporal embedding: {d}")
+        timestep = timestep.to(device=unet.device, dtype=torch.int64).reshape(-1).contiguous()
+        if timestep.numel() != B:
+            raise ValueError("timestep must have one entry per image")
+        if unet.config.enable_pose_encoder:
+            skeletons = self._bf16(skeletons, "skeletons")
+            if tuple(skeletons.shape) != (B, 3, 8 * H, 8 * W):
+                raise ValueError(f"skeletons must be [B, 3, 8H, 8W], got {tuple(skeletons.shape)}")
+        else:
+            skeletons = None
         dom = (C.c_int32 * len(domains))(*[_DOMAIN_IDS[d] for d in domains])
         out = torch.empty(B, unet.config.out_channels, H, W, device=unet.device, dtype=torch.bfloat16)
         with torch.cuda.device(unet.device):
@@ -71,9 +103,17 @@ class FrameShardedPipeline:
                        timestep_indices, domain: str, guidance_scale: float, F_total: int, num_inference_steps: int = 1):
         """B-3 on this rank's frames (all tensors hold the LOCAL frames; updated in place like the single-GPU call)."""
         pipe = self.pipe
+        if domain not in _DOMAIN_IDS:
+            raise ValueError(f"Invalid domain for temporal embedding: {domain}")
+        self._inplace(latents, "latents", torch.bfloat16)
+        self._inplace(timestep_indices, "timestep_indices", torch.int64)
         F_local, _, h, w = latents.shape
         if F_local * self.world != F_total:
             raise ValueError(f"F_total ({F_total}) must equal world ({self.world}) * local frames ({F_local})")
+        pixel_values_latents = self._bf16(pixel_values_latents, "pixel_values_latents")
+        plucker_embeds_latents = self._bf16(plucker_embeds_latents, "plucker_embeds_latents")
+        skeletons_latents = self._bf16(skeletons_latents, "skeletons")
+        cond_masks_latents = self._bf16(cond_masks_latents, "cond_masks_latents")
         sched = pipe.scheduler.c_struct(pipe.emulate_bf16_scheduler)
         with torch.cuda.device(pipe.device):
             check(lib().d4d_denoise_window_sharded(

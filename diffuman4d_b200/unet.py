@@ -158,6 +158,31 @@ class B200MultiviewUNet:
 
     __call__ = forward
 
+    def debug_taps(self, sample, timestep, skeletons=None, domains=None, num_frames: int = 1) -> Dict[str, torch.Tensor]:
+        """Intermediate activations for drift reports: {"conv_in", "down_blocks.i", "mid_block", "up_blocks.i"} -> NCHW bf16.
+        One (prefix of a) forward is run per tap (``d4d_debug_tap``); same argument checks as ``forward``."""
+        cfg = self.config
+        B, _, H, W = sample.shape
+        dom = (C.c_int32 * len(domains))(*[_DOMAIN_IDS[d] for d in domains])
+        sample = sample.to(device=self._device, dtype=torch.bfloat16).contiguous()
+        timestep = timestep.to(device=self._device, dtype=torch.int64).reshape(-1).contiguous()
+        if cfg.enable_pose_encoder:
+            skeletons = skeletons.to(device=self._device, dtype=torch.bfloat16).contiguous()
+        sk_ptr = skeletons.data_ptr() if cfg.enable_pose_encoder else None
+        out: Dict[str, torch.Tensor] = {}
+        name, dims = C.create_string_buffer(64), (C.c_int32 * 3)()
+        with torch.cuda.device(self._device):
+            stream = torch.cuda.current_stream().cuda_stream
+            tap = 0
+            while lib().d4d_debug_tap(self._h, sample.data_ptr(), timestep.data_ptr(), sk_ptr, dom, len(domains), B,
+                                      num_frames, H, W, tap, None, name, dims, stream) == 0:
+                t = torch.empty(B, dims[0], dims[1], dims[2], device=self._device, dtype=torch.bfloat16)
+                check(lib().d4d_debug_tap(self._h, sample.data_ptr(), timestep.data_ptr(), sk_ptr, dom, len(domains), B,
+                                          num_frames, H, W, tap, t.data_ptr(), name, dims, stream), "d4d_debug_tap")
+                out[name.value.decode()] = t
+                tap += 1
+        return out
+
     def forward_launches(self, n_domains: int, B: int, F: int, h: int, w: int) -> int:
         n = C.c_int(0)
         check(lib().d4d_forward_launches(self._h, n_domains, B, F, h, w, C.byref(n)))

@@ -137,13 +137,13 @@ int d4d_op_groupnorm(const void* x1, int C1, const void* x2, int C2, int n_img, 
                      const float* gamma, const float* beta, int silu, void* out, void* stream);
 int d4d_op_layernorm(const void* x, int rows, int C, float eps, const float* gamma, const float* beta, void* out,
                      void* stream);
-/* UMMA operand-encoding probe (tests pin the shared-memory descriptor conventions against torch.matmul) */
-int d4d_op_probe_umma(const void* A, const void* B, float* D, int N, int K, int a_src, int b_major, uint32_t b_lbo,
-                      uint32_t b_sbo, uint32_t b_kadv, void* stream);
-
-/* Device microbenchmarks that size the attention kernel: kind 0 tcgen05.ld x32, 1 tcgen05.ld x16, 2 tcgen05.st x16,
- * 3 ex2.approx (8 per iteration), 4 cvt.bf16x2 (4 per iteration); `warps` per CTA, `blocks` CTAs; cycles_dev[blocks]. */
-int d4d_microbench(int kind, int warps, int iters, int blocks, uint64_t* cycles_dev, float* sink_dev, void* stream);
+/* Debug tap (per-level drift reports in tests/): runs the forward of d4d_unet_forward up to intermediate activation
+ * `tap` (0 = conv_in(+pose), then down_blocks.0-3, mid_block, up_blocks.0-3) and copies it out as NCHW bf16
+ * [B, C, H, W].  name64 (64 bytes) / dims3 (C, H, W) are filled when non-NULL; out == NULL only queries them.
+ * Returns 1 when `tap` is out of range. */
+int d4d_debug_tap(d4d_handle* h, const void* sample, const int64_t* timestep, const void* skeletons,
+                  const int32_t* domain_ids, int n_domains, int B, int F, int height, int width, int tap, void* out,
+                  char* name64, int32_t* dims3, void* stream);
 
 /* ---- multi-GPU: frame-sharded window with fused K/V exchange over peer memory ------------
  * One process per GPU.  Rank r of `world` owns frames [r*F_local, (r+1)*F_local) of each CFG half (F_total = world *

@@ -31,6 +31,23 @@ def test_header_and_library_export_the_same_symbols(libd4d):
     assert libd4d.d4d_version() >= 100
 
 
+def test_product_library_carries_no_test_kernels_or_ablation_switches(libd4d):
+    """Library hygiene: the measurement / probe kernels and the D4D_*_ABLATE environment switches exist only in the tools
+    build libd4d_test.so (include/d4d_test.h), never in the product library."""
+    import subprocess
+    from diffuman4d_b200._lib import LIB_PATH, TEST_EXPORTS, TEST_LIB_PATH, test_lib
+    hdr = open(os.path.join(ROOT, "include", "d4d_test.h")).read()
+    assert set(re.findall(r"\b(d4d_[a-z0-9_]+)\s*\(", hdr)) == set(TEST_EXPORTS)
+    for name in TEST_EXPORTS:
+        assert not hasattr(libd4d, name), f"product library exports {name}"
+        assert hasattr(test_lib(), name)
+    prod = subprocess.run(["strings", LIB_PATH], capture_output=True, text=True).stdout
+    tools = subprocess.run(["strings", TEST_LIB_PATH], capture_output=True, text=True).stdout
+    for sw in ("D4D_GEMM_ABLATE", "D4D_ATTN_ABLATE"):
+        assert sw not in prod and sw in tools
+    assert "microbench" not in prod and "probe_kernel" not in prod
+
+
 def test_library_has_no_libcuda_or_torch_dependency(libd4d):
     import subprocess
     from diffuman4d_b200._lib import LIB_PATH
@@ -119,6 +136,39 @@ def test_window_builder_matches_oracle():
         assert len(a[0]) == len(b[0]) and all(torch.equal(x, y) for x, y in zip(a[0], b[0]))
     with pytest.raises(ValueError):
         build_windows(tgt, inp, "diagonal", 12, 2)
+
+
+def test_loader_vae_factory_resolution(tmp_path):
+    """B-1: the Hydra yaml can only carry strings, so ``vae_factory`` accepts a dotted path; the default builds the stock
+    AutoencoderKL adapter only when ``model_dir/vae`` exists."""
+    from diffuman4d_b200 import loader
+    assert loader._resolve_factory(None) is loader.default_vae_factory
+    assert loader.default_vae_factory(str(tmp_path), 0) is None                    # no vae/ directory -> latents only
+    f = loader._resolve_factory("diffuman4d_b200.loader.default_vae_factory")
+    assert f is loader.default_vae_factory
+    with pytest.raises(ValueError):
+        loader._resolve_factory("nodots")
+    with pytest.raises(ValueError):
+        loader._resolve_factory(3)
+
+    class FakeVAE:                                   # the reference's encode_vae / decode_vae arithmetic (PIPE:47-72,280-285)
+        class config:
+            scaling_factor = 0.5
+
+        def encode(self, x):
+            from types import SimpleNamespace
+            return SimpleNamespace(latent_dist=SimpleNamespace(sample=lambda: x[:, :, ::8, ::8] * 2))
+
+        def decode(self, z, return_dict=False):
+            return (z.repeat_interleave(8, 2).repeat_interleave(8, 3),)
+
+    a = loader.StockVAEAdapter(FakeVAE(), batch_size=2)
+    img = torch.rand(5, 3, 16, 16) * 2 - 1
+    z = a.encode_latents(img)
+    assert torch.equal(z, img[:, :, ::8, ::8] * 2 * 0.5)
+    out = a.decode_latents(z)
+    assert out.shape == img.shape and float(out.min()) >= 0 and float(out.max()) <= 1
+    torch.testing.assert_close(out[:, :, ::8, ::8], (img[:, :, ::8, ::8] * 2 / 2 + 0.5).clamp(0, 1))
 
 
 def test_loader_config_mapping():

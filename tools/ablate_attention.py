@@ -3,6 +3,8 @@ kernel are switched off (results are then wrong) to see what the time is sensiti
 import os
 import sys
 
+os.environ["D4D_USE_TEST_LIB"] = "1"   # the ablation switches exist only in the tools build (libd4d_test.so)
+
 import torch
 
 sys.path.insert(0, ".")

@@ -5,6 +5,8 @@ Results are garbage by construction; only the device time matters.  One process 
 import os
 import sys
 
+os.environ["D4D_USE_TEST_LIB"] = "1"   # the ablation switches exist only in the tools build (libd4d_test.so)
+
 import torch
 
 sys.path.insert(0, ".")

@@ -4,7 +4,7 @@ import sys
 import torch
 
 sys.path.insert(0, ".")
-from diffuman4d_b200._lib import check, lib  # noqa: E402
+from diffuman4d_b200._lib import check, test_lib as lib  # noqa: E402  (tools build: libd4d_test.so)
 
 cyc = torch.zeros(148, dtype=torch.int64, device="cuda")
 sink = torch.zeros(4, device="cuda")
