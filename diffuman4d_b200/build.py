@@ -21,9 +21,9 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_obj")
 LIB = os.path.join(HERE, "libd4d.so")
 TEST_LIB = os.path.join(HERE, "libd4d_test.so")
-SOURCES = ["tmap.cu", "gemm_umma.cu", "attention_umma.cu", "norm.cu", "elementwise.cu", "unet.cu", "d4d_api.cu"]
+SOURCES = ["tmap.cu", "gemm_umma.cu", "attention_umma.cu", "attention_d64.cu", "norm.cu", "elementwise.cu", "unet.cu", "d4d_api.cu"]
 TEST_SOURCES = SOURCES + ["probe.cu", "microbench.cu"]
-TEST_DEFS = ["-DD4D_TEST_KERNELS", "-DD4D_ABLATE"]
+TEST_DEFS = ["-DD4D_TEST_KERNELS", "-DD4D_ABLATE", "-DD4D_SPIN_LIMIT=(1u<<21)"]  # tools build: a protocol bug traps within seconds
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC",
          "-diag-suppress", "177"]

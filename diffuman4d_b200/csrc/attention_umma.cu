@@ -487,6 +487,20 @@ int launch_attn(const AttnLaunch& L, cudaStream_t stream) {
 
 }  // namespace
 
+// tools build only: D4D_ATTN_GENERIC=1 routes head_dim 64 through the generic kernel (A/B timing, tools/bench_attention.py)
+static inline bool attn_generic_forced() {
+#ifdef D4D_ABLATE
+  const char* e = getenv("D4D_ATTN_GENERIC");
+  return e && e[0] == '1';
+#else
+  return false;
+#endif
+}
+
+// head_dim 64 has its own kernel (attention_d64.cu): 256-row CTAs, 128-key tiles, split MUFU / FMA-pipe exp2
+int attn64_prepare(const AttnDesc& d, AttnLaunch* L);
+int attn64_run(const AttnLaunch& L, cudaStream_t stream);
+
 int attn_prepare(const AttnDesc& d, AttnLaunch* L) {
   D4D_REQUIRE(d.head_dim == 64 || d.head_dim == 128 || d.head_dim == 192,
               "attention head_dim (after padding) must be 64, 128 or 192");
@@ -494,6 +508,11 @@ int attn_prepare(const AttnDesc& d, AttnLaunch* L) {
   D4D_REQUIRE(d.ld_qkv % 8 == 0 && d.ld_out % 8 == 0 && d.ld_kv % 8 == 0, "leading dimensions must be multiples of 8");
   D4D_REQUIRE(d.scale > 0.f, "softmax scale must be positive");
   L->d = d;
+  if (d.head_dim == 64 && !attn_generic_forced()) {
+    if (int rc = attn64_prepare(d, L)) return rc;  // sets variant 0 / -1 (kernel shape)
+    D4D_REQUIRE(L->grid_y <= 65535, "batch*heads exceeds grid.y limit");
+    return 0;
+  }
   L->variant = d.head_dim / 64;
   const int seq_kv = d.seq_kv > 0 ? d.seq_kv : d.seq;
   const int ld_kv = d.ld_kv > 0 ? d.ld_kv : d.ld_qkv;
@@ -511,6 +530,8 @@ int attn_prepare(const AttnDesc& d, AttnLaunch* L) {
 
 int attn_run(const AttnLaunch& L, cudaStream_t stream) {
   switch (L.variant) {
+    case 0:
+    case -1: return attn64_run(L, stream);
     case 1: return launch_attn<1>(L, stream);
     case 2: return launch_attn<2>(L, stream);
     case 3: return launch_attn<3>(L, stream);

@@ -113,6 +113,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Same bound without the printf: vprintf is a real call, and a call in a warp that holds > 128 live registers (the
+// head_dim-64 attention softmax) makes ptxas save them around it; the trap alone still turns a protocol bug into
+// cudaErrorLaunchFailure instead of a hang.
+__device__ __forceinline__ void mbar_wait_quiet(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > D4D_SPIN_LIMIT) __trap();
+  }
+}
+
 // ---- proxies / fences ----------------------------------------------------------------------
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

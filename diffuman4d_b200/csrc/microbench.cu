@@ -168,9 +168,79 @@ __global__ void microbench_kernel(int kind, int iters, unsigned long long* cycle
   }
 }
 
+// Issue-rate probes of the CUDA-core pipes the attention softmax leans on (kinds 100+): every thread runs 8 independent
+// dependency chains of one instruction type; cycles / (8 * iters * warps per sub-partition) = cycles per warp instruction.
+template <int kind>
+__global__ void pipe_bench_kernel(int iters, unsigned long long* cycles, float* sink, unsigned one) {
+  float x[8];
+  uint64_t y[8];
+  uint32_t u[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    x[k] = -0.001f * (threadIdx.x + k) - 0.5f;
+    y[k] = f2_pack(0.5f + 0.001f * k, 0.25f + 0.001f * threadIdx.x);
+    u[k] = threadIdx.x * 7 + k;
+  }
+  const uint64_t ca = f2_pack(0.999f, 1.001f), cb = f2_pack(0.0001f, -0.0001f);
+  __syncthreads();
+  const unsigned long long t0 = clock64();
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      switch (kind) {
+        case 100: asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(x[k])); break;
+        case 101: asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(u[k]) : "f"(x[k]), "f"(x[(k + 1) & 7])); break;
+        case 102: asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(y[k]) : "l"(ca), "l"(cb)); break;
+        case 103: asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(y[k]) : "l"(cb)); break;
+        case 104: asm volatile("max.f32 %0, %0, %1, %2;" : "+f"(x[k]) : "f"(x[(k + 1) & 7]), "f"(x[(k + 2) & 7])); break;
+        case 105: asm volatile("mad.lo.u32 %0, %0, %1, 0x8000;" : "+r"(u[k]) : "r"(one)); break;
+        case 106: asm volatile("prmt.b32 %0, %0, %1, 0x7632;" : "+r"(u[k]) : "r"(u[(k + 1) & 7])); break;
+        case 107: asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(x[k]) : "f"(0.999f), "f"(0.0001f)); break;
+        case 108:
+          asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(x[k]));
+          asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(y[k]) : "l"(ca), "l"(cb));
+          break;
+        case 109: asm volatile("max.f32 %0, %0, %1;" : "+f"(x[k]) : "f"(x[(k + 1) & 7])); break;
+        case 110: asm volatile("add.rm.f32x2 %0, %0, %1;" : "+l"(y[k]) : "l"(cb)); break;
+        case 111:  // the v0 pair: FFMA2, 2 MUFU, FADD2, F2FP
+          asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(y[k]) : "l"(ca), "l"(cb));
+          asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(x[k]));
+          asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(x[(k + 4) & 7]));
+          asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(y[(k + 4) & 7]) : "l"(cb));
+          asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(u[k]) : "f"(x[k]), "f"(x[(k + 1) & 7]));
+          break;
+        case 112: asm volatile("add.u32 %0, %0, 0x8000;" : "+r"(u[k])); break;
+        default: break;
+      }
+    }
+  }
+  __syncthreads();
+  const unsigned long long t1 = clock64();
+  if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+  float acc = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    float a, b;
+    f2_unpack(y[k], a, b);
+    acc += x[k] + a + b + __uint_as_float(u[k]);
+  }
+  if (acc == 12345.678f) sink[0] = acc;
+}
+
 }  // namespace
 
 int microbench_run(int kind, int warps, int iters, int blocks, unsigned long long* cycles_dev, float* sink_dev, cudaStream_t s) {
+  if (kind >= 100) {
+    D4D_REQUIRE(kind <= 112 && warps >= 1 && warps <= 32 && iters > 0 && blocks > 0, "microbench arguments");
+#define D4D_PB(K) case K: pipe_bench_kernel<K><<<blocks, warps * 32, 0, s>>>(iters, cycles_dev, sink_dev, 1u); break;
+    switch (kind) {
+      D4D_PB(100) D4D_PB(101) D4D_PB(102) D4D_PB(103) D4D_PB(104) D4D_PB(105) D4D_PB(106) D4D_PB(107) D4D_PB(108) D4D_PB(109)
+      D4D_PB(110) D4D_PB(111) D4D_PB(112)
+    }
+#undef D4D_PB
+    D4D_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
   D4D_REQUIRE(kind >= 0 && kind <= 24 && warps >= 1 && warps <= 16 && iters > 0 && blocks > 0, "microbench arguments");
   microbench_kernel<<<blocks, warps * 32, 0, s>>>(kind, iters, cycles_dev, sink_dev);
   D4D_CUDA_OK(cudaGetLastError());
