@@ -103,7 +103,8 @@ __device__ __forceinline__ int ord_v(int t, int n_tiles) { return n_tiles == 1 ?
 //            log2(1.0028) so that E[trunc(P')] = P, and the row sum (taken from the un-truncated P') is divided by the
 //            same factor in the epilogue.  |error| <= 0.28 % per element against 0.2 % of round-to-nearest.
 // (Measured and dropped, profiles/README.md: integer round-half-up packing on the ALU pipe or with IMAD on the FMA pipe,
-//  a fused round-down FFMA2 for the polynomial's floor, keeping P in registers until chunk 1 / the end of the tile.)
+//  a fused round-down FFMA2 for the polynomial's floor, keeping P in registers until chunk 1 / the end of the tile,
+//  shared-memory hand-off counters and overlapped barrier probes in the MMA warp, a head start for one Q tile.)
 struct Variant { uint32_t poly_mask; bool trunc; };
 __host__ __device__ constexpr Variant variant_of(int v) {
   return v == 0 ? Variant{0x00, false}
@@ -315,10 +316,10 @@ attn64_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         const int j = next[q];
         if (j >= n_tiles) continue;
         all_done = false;
-        if (!__all_sync(0xffffffffu, mbar_test(&tile_done[q], (j + 1) & 1))) continue;
         const bool has_pv = j >= 0, has_qk = j + 2 < n_tiles;
         // never block on the ring here: a slot this Q tile waits for may only be refilled after ANOTHER Q tile has been
         // served (it releases the slot's previous occupant)
+        if (!__all_sync(0xffffffffu, mbar_test(&tile_done[q], (j + 1) & 1))) continue;
         if (has_pv && !tile_landed(ord_v(j, n_tiles))) continue;
         if (has_qk && !tile_landed(ord_k(j + 2))) continue;
         progress = true;
@@ -395,11 +396,13 @@ attn64_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
       constexpr bool kMasked = decltype(masked_tag)::value;
       const bool has_next = j + 1 < n_tiles;
       // P_q is free once P.V(q, j-1) has completed; S_q(j+1) complete implies that (commit order in the MMA warp).
-      // Probe now, wait (if at all) right before the first P store.
+      // Looking at an mbarrier costs ~250 cycles even when its phase is complete, so it is PROBED twice without
+      // consuming the answer (here and after the row max) and the answers are consumed right before the first P store:
+      // the probes' latencies hide behind the row max and the exponentials of chunk 0.
       uint64_t* free_bar = has_next ? &s_full[q] : &pv_done[q];
       const uint32_t free_par = has_next ? ((j + 1) & 1) : ((j - 1) & 1);
       const bool need_free = has_next || j > 0;
-      const bool p_free = !need_free || __all_sync(0xffffffffu, mbar_test(free_bar, free_par));
+      const bool probe0 = !need_free || mbar_test(free_bar, free_par);
 #ifdef D4D_ATTN_TRACE
       if (j >= 64) tr = nullptr;
 #endif
@@ -435,6 +438,7 @@ attn64_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         rescale_o(alpha);
       }
       l *= alpha;  // l == 0 for tile 0
+      const bool probe1 = probe0 || mbar_test(free_bar, free_par);
       D4D_TRACE(1);
 
       // ---- P = exp2(S * scale - m), chunks of 32 columns ----
@@ -446,7 +450,7 @@ attn64_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
           ExpChunk<VAR, kMasked, KV, c>::run(sv, pk, sc2, nm2, lsum, valid);
           if (c == 0) D4D_TRACE(2);
           if (c == 0 && need_free) {
-            if (!p_free) mbar_wait_quiet(free_bar, free_par);
+            if (!__all_sync(0xffffffffu, probe1)) mbar_wait_quiet(free_bar, free_par);
             tc_fence_after();
           }
           D4D_TRACE(3 + c);
