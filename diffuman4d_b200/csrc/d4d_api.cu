@@ -289,6 +289,36 @@ int d4d_op_groupnorm(const void* x1, int C1, const void* x2, int C2, int n_img, 
   D4D_API_END
 }
 
+int d4d_op_conv3x3_groupnorm(const void* x_nhwc, int n_img, int H, int W, int Cin, const void* Wt, int Cout, const float* bias,
+                             const void* residual, int groups, float eps, const float* gamma, const float* beta, int silu,
+                             void* conv_out, void* gn_out, void* stream) {
+  D4D_API_BEGIN
+  D4D_REQUIRE(n_img > 0 && H > 0 && W > 0 && groups > 0, "empty conv");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t floats = static_cast<size_t>(n_img) * Cout * 2 * 2;  // [n_img][Cout][2] 64-bit {sum, sumsq}
+  // accumulated by the conv epilogue; lives behind the stand-alone kernel's scratch (16-byte aligned for the 128-bit loads)
+  const size_t off = (d4d::groupnorm_scratch_floats(n_img, groups) + 3) & ~size_t(3);
+  float* base = gn_scratch(off + floats);
+  if (!base) {
+    d4d::set_error("GroupNorm scratch allocation failed");
+    return 2;
+  }
+  long long* stats = reinterpret_cast<long long*>(base + off);
+  D4D_CUDA_OK(cudaMemsetAsync(stats, 0, floats * sizeof(float), st));
+  d4d::GemmDesc d;
+  d.conv = 1; d.A = static_cast<const bf16*>(x_nhwc); d.n_img = n_img; d.H = H; d.W = W; d.Cin = Cin;
+  d.Wt = static_cast<const bf16*>(Wt); d.N = Cout; d.bias = bias;
+  d.residual = static_cast<const bf16*>(residual); d.ld_res = Cout;
+  d.out = static_cast<bf16*>(conv_out); d.ldo = Cout;
+  d.stats = stats;
+  d4d::GemmLaunch L;
+  if (int rc = d4d::gemm_prepare(d, &L)) return rc;
+  if (int rc = d4d::gemm_run(L, st)) return rc;
+  return d4d::groupnorm_apply_run(static_cast<const bf16*>(conv_out), Cout, stats, nullptr, 0, nullptr, n_img, H * W, groups, eps,
+                                  gamma, beta, silu, static_cast<bf16*>(gn_out), st);
+  D4D_API_END
+}
+
 int d4d_op_layernorm(const void* x, int rows, int C, float eps, const float* gamma, const float* beta, void* out,
                      void* stream) {
   D4D_API_BEGIN

@@ -78,6 +78,36 @@ __device__ __forceinline__ void add8_bf16(float* f, const uint4& u) {
   p = unpack_bf16x2(u.w); f[6] += p.x; f[7] += p.y;
 }
 
+// Column sums over the 32 rows of a warp for 16 columns held one row per lane: a butterfly that halves the number of
+// columns a lane keeps at every step (8 + 4 + 2 + 1 + 1 shuffles).  Returns, in every lane, the total of column
+// (lane >> 1) & 15 ... precisely: bit 4 of the lane selects columns 8-15, bit 3 the upper 4 of those, bit 2, bit 1.
+__device__ __forceinline__ float colsum16(float (&v)[16], int lane) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const bool up = lane & 16;
+    const float send = up ? v[i] : v[i + 8], keep = up ? v[i + 8] : v[i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const bool up = lane & 8;
+    const float send = up ? v[i] : v[i + 4], keep = up ? v[i + 4] : v[i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const bool up = lane & 4;
+    const float send = up ? v[i] : v[i + 2], keep = up ? v[i + 2] : v[i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  {
+    const bool up = lane & 2;
+    const float send = up ? v[0] : v[1], keep = up ? v[1] : v[0];
+    v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+  return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
 template <bool kGeglu>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_a2,
@@ -332,6 +362,11 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             for (int i = 0; i < 4; ++i) b4[i] = __ldg(bp + i);
           }
           tmem_ld_wait();
+          float sv[16];  // stats: the rounded outputs of this thread's row (zero for rows outside the tensor)
+          if (a.stats) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) sv[i] = 0.f;
+          }
           if (valid) {
             float f[16];
 #pragma unroll
@@ -352,6 +387,10 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               for (int i = 0; i < 16; ++i) f[i] *= a.out_scale;
             }
             if (a.residual) { add8_bf16(f, r0); add8_bf16(f + 8, r1); }
+            if (a.stats) {  // statistics of what is stored: round to bf16 first
+#pragma unroll
+              for (int i = 0; i < 16; ++i) sv[i] = f[i] = __bfloat162float(__float2bfloat16_rn(f[i]));
+            }
             uint4 o0, o1;
             o0.x = pack_bf16x2(f[0], f[1]);   o0.y = pack_bf16x2(f[2], f[3]);
             o0.z = pack_bf16x2(f[4], f[5]);   o0.w = pack_bf16x2(f[6], f[7]);
@@ -375,6 +414,22 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               uint4* op = reinterpret_cast<uint4*>(a.out + static_cast<size_t>(row) * a.ldo + col);
               op[0] = o0;
               op[1] = o1;
+            }
+          }
+          if (a.stats) {
+            // GroupNorm statistics of the output: column sums over this warp's 32 rows (they belong to ONE image:
+            // gemm_prepare checks it), one red.global per (column, moment) and warp.  Lane 0 holds the first row / the
+            // tile's minimal (x, y): when it is outside the tensor the whole warp is.
+            float sq[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) sq[i] = sv[i] * sv[i];
+            const float cs = colsum16(sv, lane), cq = colsum16(sq, lane);
+            const int cc = ((lane & 16) ? 8 : 0) + ((lane & 8) ? 4 : 0) + ((lane & 4) ? 2 : 0) + ((lane & 2) ? 1 : 0);
+            const int img0 = __shfl_sync(0xffffffffu, a.mode == 0 ? static_cast<int>(row / a.stats_rows) : img, 0);
+            if (__shfl_sync(0xffffffffu, valid ? 1 : 0, 0)) {
+              const long long fx = __float2ll_rn((lane & 1) ? cq * kGnSqScale : cs * kGnSumScale);  // fixed point: order-free
+              atomicAdd(reinterpret_cast<unsigned long long*>(a.stats) + (static_cast<size_t>(img0) * a.N + col + cc) * 2 + (lane & 1),
+                        static_cast<unsigned long long>(fx));
             }
           }
           if (!direct && ((k & 1) || c + 1 >= chunks)) flush((k & 1) ? 4 : 2, n0 + (c & ~1) * 16);
@@ -489,6 +544,10 @@ int gemm_prepare(const GemmDesc& d, GemmLaunch* L) {
   a.geglu = d.geglu;
   a.act = d.act;
   a.out_scale = d.out_scale;
+  a.stats = d.stats;
+  a.stats_rows = d.stats_rows > 0 ? d.stats_rows : 1;
+  D4D_REQUIRE(d.stats == nullptr || (!d.geglu && d.kv_world == 0), "GroupNorm statistics: plain / conv epilogue only");
+  D4D_REQUIRE(d.stats == nullptr || d.conv || (d.stats_rows > 0 && d.stats_rows % 32 == 0), "statistics need rows-per-image % 32 == 0");
   a.kv_world = d.kv_world;
   a.kv_col0 = d.kv_col0;
   a.kv_ld = d.kv_ld;
@@ -531,6 +590,7 @@ int gemm_prepare(const GemmDesc& d, GemmLaunch* L) {
     // H, W need not be powers of two: the tile may overhang, TMA zero-fills and the epilogue masks
     int bnimg = 128 / (bw * bh);
     D4D_REQUIRE(bw * bh * bnimg == 128 && bnimg <= 256, "conv tile shape");
+    D4D_REQUIRE(d.stats == nullptr || (bw * bh) % 32 == 0, "statistics need 32-row warps inside one image");
     a.BW = bw; a.BH = bh; a.BN = bnimg;
     a.tiles_x = (d.W + bw - 1) / bw;
     a.tiles_y = (d.H + bh - 1) / bh;

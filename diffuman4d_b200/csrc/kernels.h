@@ -13,6 +13,11 @@ namespace d4d {
 // --------------------------------------------------------------------------------------------
 // tcgen05 GEMM / implicit-GEMM conv3x3  (gemm_umma.cu)
 // --------------------------------------------------------------------------------------------
+// fixed-point scales of the fused GroupNorm statistics: |sum| < 2^35 (|x| <= 2e6 over 16384 pixels), sum of squares < 2^39
+// (rms |x| <= 5800 over 16384 pixels); resolutions 3.7e-9 / 6e-8 per 32-row partial
+constexpr float kGnSumScale = 268435456.f;  // 2^28
+constexpr float kGnSqScale = 16777216.f;    // 2^24
+
 struct GemmKernelArgs {
   int dbg;  // ablation switches (tools/ablate_gemm.py); 0 in production
   int M, N, k_blocks, block_n, n_tiles, m_tiles;
@@ -29,6 +34,12 @@ struct GemmKernelArgs {
   int geglu;
   int act;          // 0 none, 1 SiLU applied to (acc + bias + rowvec) before scale/residual
   float out_scale;  // multiplies (acc + bias + rowvec) after the activation
+  // fused GroupNorm statistics of the OUTPUT tensor: per (image, column) sum and sum of squares in 64-bit FIXED POINT
+  // (kGnSumScale / kGnSqScale), accumulated with red.global.add.u64 into stats[(image * N + column) * 2 + {0, 1}] (zeroed by
+  // the caller); image = row / stats_rows.  Integer adds commute, so the result does not depend on the order in which the
+  // tiles finish: repeated forwards and the frame-sharded window stay bit-identical (float atomics would not).
+  long long* stats;
+  int stats_rows;
   // fused K/V all-gather (frame-sharded window): columns >= kv_col0 are stored into every rank's gathered buffer
   int kv_world, kv_col0, kv_ld;
   long long kv_rows_local, kv_rows_global, kv_row_offset;
@@ -54,6 +65,9 @@ struct GemmDesc {
   int act = 0;
   float out_scale = 1.0f;
   int block_n = 0;  // 0 = auto
+  // GroupNorm statistics of the output (see GemmKernelArgs::stats); plain GEMM: stats_rows = rows per image
+  long long* stats = nullptr;
+  int stats_rows = 0;
   // fused K/V all-gather: rows of CFG half h (local row / kv_rows_local) land at global row
   // h*kv_rows_global + kv_row_offset + (local row % kv_rows_local) of every kv_dst[r] (leading dim kv_ld)
   int kv_world = 0, kv_col0 = 0, kv_ld = 0;
@@ -119,6 +133,12 @@ inline size_t groupnorm_scratch_floats(int n_img, int groups) {
 }
 int groupnorm_run(const bf16* x1, int C1, const bf16* x2, int C2, int n_img, int hw, int groups, float eps,
                   const float* gamma, const float* beta, int silu, bf16* out, float* partials, cudaStream_t stream);
+// Same normalisation with the statistics taken from the per-(image, channel) {sum, sum of squares} arrays that the
+// producing GEMM / conv epilogue accumulated (GemmDesc::stats): one launch, one read of x, no statistics pass.
+// stats1: [n_img][C1][2], stats2: [n_img][C2][2] (null when C2 == 0), fixed point (kGnSumScale, kGnSqScale).
+int groupnorm_apply_run(const bf16* x1, int C1, const long long* stats1, const bf16* x2, int C2, const long long* stats2, int n_img,
+                        int hw, int groups, float eps, const float* gamma, const float* beta, int silu, bf16* out,
+                        cudaStream_t stream);
 // LayerNorm over rows of width C (C % 8 == 0, C <= 2048)
 int layernorm_run(const bf16* x, int rows, int C, float eps, const float* gamma, const float* beta, bf16* out,
                   cudaStream_t stream);

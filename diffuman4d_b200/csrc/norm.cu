@@ -31,6 +31,10 @@ struct GnArgs {
   float* partials;  // [n_img][splits][groups][2] = (mean, M2)
   float* final_stats;   // [n_img][groups][2] = (mean, rstd), written by the last stats CTA of each image
   unsigned int* counters;  // [n_img] arrival counters (self-resetting)
+  // fused-statistics mode (groupnorm_apply_run): per-(image, channel) {sum, sum of squares} of each source, accumulated by
+  // the epilogue of the GEMM / conv that produced it (gemm_umma.cu); the apply kernel derives (mean, rstd) itself
+  const long long* ch_stats1;  // fixed point (kGnSumScale, kGnSqScale)
+  const long long* ch_stats2;
 };
 
 __device__ __forceinline__ uint4 gn_load(const GnArgs& a, int img, int pixel, int oct) {
@@ -181,8 +185,35 @@ __global__ void __launch_bounds__(GN_MAX_THREADS, 2) gn_apply_kernel(const GnArg
   const int split = blockIdx.x, img = blockIdx.y;
   pdl_wait();
   pdl_launch_dependents();
-  for (int g = threadIdx.x; g < 2 * a.groups; g += blockDim.x)
-    sm[(g & 1) * a.groups + (g >> 1)] = a.final_stats[static_cast<size_t>(img) * a.groups * 2 + g];
+  if (a.ch_stats1 == nullptr) {
+    for (int g = threadIdx.x; g < 2 * a.groups; g += blockDim.x)
+      sm[(g & 1) * a.groups + (g >> 1)] = a.final_stats[static_cast<size_t>(img) * a.groups * 2 + g];
+  } else {
+    // one warp per group: sum the group's channels' {sum, sumsq} (the virtual concat may straddle the two sources)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    for (int g = warp < nwarps ? warp : a.groups; g < a.groups; g += nwarps) {  // (a trailing partial warp sits out)
+      long long s = 0, q = 0;  // exact integer sums of the fixed-point channel totals
+      for (int i = lane; i < a.cpg; i += 32) {
+        const int c = g * a.cpg + i;
+        const longlong2 v = c < a.C1 ? __ldcg(reinterpret_cast<const longlong2*>(a.ch_stats1) + static_cast<size_t>(img) * a.C1 + c)
+                                     : __ldcg(reinterpret_cast<const longlong2*>(a.ch_stats2) + static_cast<size_t>(img) * a.C2 + (c - a.C1));
+        s += v.x;
+        q += v.y;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        q += __shfl_xor_sync(0xffffffffu, q, o);
+      }
+      if (lane == 0) {  // 32 groups per CTA: double precision keeps E[x^2] - mean^2 exact up to the fixed-point resolution
+        const double inv_n = 1.0 / (static_cast<double>(a.cpg) * static_cast<double>(a.hw));
+        const double mean = static_cast<double>(s) * (1.0 / static_cast<double>(kGnSumScale)) * inv_n;
+        const double var = fmax(static_cast<double>(q) * (1.0 / static_cast<double>(kGnSqScale)) * inv_n - mean * mean, 0.0);
+        sm[g] = static_cast<float>(mean);
+        sm[a.groups + g] = rsqrtf(static_cast<float>(var) + a.eps);
+      }
+    }
+  }
   __syncthreads();
   const int oct = threadIdx.x % a.n_oct;
   const int prow = threadIdx.x / a.n_oct;
@@ -326,6 +357,7 @@ int groupnorm_run(const bf16* x1, int C1, const bf16* x2, int C2, int n_img, int
   a.cpg = C / groups;
   a.eps = eps;
   a.gamma = gamma; a.beta = beta; a.silu = silu; a.out = out; a.partials = partials;
+  a.ch_stats1 = a.ch_stats2 = nullptr;
   // scratch layout: partials | final stats | counters (counters must be zero before first use; they self-reset)
   a.final_stats = partials + static_cast<size_t>(n_img) * 32 * groups * 2;
   a.counters = reinterpret_cast<unsigned int*>(a.final_stats + static_cast<size_t>(n_img) * groups * 2);
@@ -335,6 +367,38 @@ int groupnorm_run(const bf16* x1, int C1, const bf16* x2, int C2, int n_img, int
   D4D_REQUIRE(smem_stats <= 48 * 1024, "GroupNorm stats smem");
   D4D_CUDA_OK(launch_pdl(gn_stats_kernel, grid, dim3(threads), smem_stats, stream, a));
   D4D_CUDA_OK(cudaGetLastError());
+  D4D_CUDA_OK(launch_pdl(gn_apply_kernel, grid, dim3(threads), sizeof(float) * 2 * groups, stream, a));
+  D4D_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int groupnorm_apply_run(const bf16* x1, int C1, const long long* stats1, const bf16* x2, int C2, const long long* stats2, int n_img,
+                        int hw, int groups, float eps, const float* gamma, const float* beta, int silu, bf16* out,
+                        cudaStream_t stream) {
+  if (x2 == nullptr) C2 = 0;
+  const int C = C1 + C2;
+  D4D_REQUIRE(C1 % 8 == 0 && C2 % 8 == 0 && C % groups == 0, "GroupNorm channel counts");
+  D4D_REQUIRE(C / 8 <= GN_MAX_THREADS, "GroupNorm supports at most 4096 channels");
+  D4D_REQUIRE(n_img > 0 && hw > 0 && n_img <= 65535, "GroupNorm batch");
+  D4D_REQUIRE(stats1 != nullptr && (C2 == 0 || stats2 != nullptr), "GroupNorm statistics arrays");
+  GnArgs a;
+  memset(&a, 0, sizeof(a));
+  a.x1 = x1; a.x2 = x2; a.C1 = C1; a.C2 = C2; a.C = C;
+  a.n_oct = C / 8;
+  a.rows_per_iter = GN_MAX_THREADS / a.n_oct;
+  if (a.rows_per_iter < 1) a.rows_per_iter = 1;
+  if (a.rows_per_iter > 8) a.rows_per_iter = 8;
+  a.hw = hw;
+  a.splits = groupnorm_splits(hw);
+  a.pps = (hw + a.splits - 1) / a.splits;
+  a.groups = groups;
+  a.cpg = C / groups;
+  a.eps = eps;
+  a.gamma = gamma; a.beta = beta; a.silu = silu; a.out = out;
+  a.ch_stats1 = stats1; a.ch_stats2 = stats2;
+  const int threads = a.n_oct * a.rows_per_iter;
+  D4D_REQUIRE(threads >= 32, "GroupNorm needs at least 32 threads");
+  dim3 grid(a.splits, n_img);
   D4D_CUDA_OK(launch_pdl(gn_apply_kernel, grid, dim3(threads), sizeof(float) * 2 * groups, stream, a));
   D4D_CUDA_OK(cudaGetLastError());
   return 0;

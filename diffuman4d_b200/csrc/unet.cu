@@ -475,12 +475,32 @@ int Model::finalize() {
 // plan builder
 // =================================================================================================
 class PlanBuilder {
+  static long long* dry_stats_marker() {  // dry run: "has statistics" marker, never dereferenced
+    static long long marker;
+    return &marker;
+  }
  public:
   PlanBuilder(Model& m, Plan& p, bool dry, char* base) : m_(m), p_(p), dry_(dry), base_(base) {}
 
-  struct Act { bf16* p; int C, H, W; };
+  struct Act { bf16* p; int C, H, W; long long* stats = nullptr; };  // stats: [B][C][2] {sum, sumsq} filled by the producer's epilogue
 
   size_t peak() const { return peak_; }
+  size_t stats_words() const { return stats_used_; }
+  // per-(image, channel) statistics of a GEMM / conv output that a GroupNorm will read: a slice of one pool that a single
+  // memset at the head of the plan zeroes
+  // (only when every 32-row warp of the producer's tiles stays inside one image: true for every level of a >= 32x32
+  //  latent; smaller test shapes fall back to the stand-alone statistics kernel)
+  long long* stats_alloc(int n_img, int C, int H, int W) {
+    int bw = 16;
+    while (bw > W) bw >>= 1;
+    int bh = 128 / bw;
+    while (bh > H && bh > 1) bh >>= 1;
+    if ((bw * bh) % 32 != 0 || (H * W) % 32 != 0) return nullptr;
+    const size_t n = static_cast<size_t>(n_img) * C * 2;
+    long long* p = stats_pool_ ? stats_pool_ + stats_used_ : dry_stats_marker();
+    stats_used_ += n;
+    return p;
+  }
   int rc() const { return rc_; }
 
   bf16* alloc(size_t elems) {
@@ -545,57 +565,68 @@ class PlanBuilder {
     if (int rc = attn_prepare(d, &L)) { if (!rc_) rc_ = rc; return; }
     op([L](cudaStream_t s) { return attn_run(L, s); }, 1, 2, attn_flops(d));
   }
-  void groupnorm(const bf16* x1, int C1, const bf16* x2, int C2, int n_img, int hw, float eps, const NormW& n, int silu, bf16* out) {
-    float* part = gn_partials_;
-    const int groups = m_.cfg_.norm_num_groups;
-    op([=](cudaStream_t s) { return groupnorm_run(x1, C1, x2, C2, n_img, hw, groups, eps, n.g, n.b, silu, out, part, s); }, 2, 3);
+  // GroupNorm(+SiLU) of (a | b): statistics come from the producers' epilogues (Act::stats), one apply launch
+  void groupnorm(const Act& xa, const Act* xb, int n_img, float eps, const NormW& n, int silu, bf16* out) {
+    const int groups = m_.cfg_.norm_num_groups, hw = xa.H * xa.W;
+    const bf16 *x1 = xa.p, *x2 = xb ? xb->p : nullptr;
+    const int C1 = xa.C, C2 = xb ? xb->C : 0;
+    const long long *s1 = xa.stats, *s2 = xb ? xb->stats : nullptr;
+    if (s1 == nullptr || (xb && s2 == nullptr)) {  // small shapes: stand-alone statistics pass
+      float* part = gn_partials_;
+      op([=](cudaStream_t s) { return groupnorm_run(x1, C1, x2, C2, n_img, hw, groups, eps, n.g, n.b, silu, out, part, s); }, 2, 3);
+      return;
+    }
+    op([=](cudaStream_t s) { return groupnorm_apply_run(x1, C1, s1, x2, C2, s2, n_img, hw, groups, eps, n.g, n.b, silu, out, s); }, 1, 3);
   }
   void layernorm(const bf16* x, int rows, int C, const NormW& n, bf16* out) {
     op([=](cudaStream_t s) { return layernorm_run(x, rows, C, 1e-5f, n.g, n.b, out, s); }, 1, 4);
   }
 
   // ResnetBlock2D on (xa | xb) -> new buffer   (reference semantics: SURVEY R-1)
-  Act resnet(const ResnetW& r, Act xa, const bf16* xb, int Cb, const bf16* temb_all, int ld_temb) {
+  Act resnet(const ResnetW& r, Act xa, const Act* xb, const bf16* temb_all, int ld_temb) {
     const int B = p_.B, hw = xa.H * xa.W, M = B * hw;
+    const int Cb = xb ? xb->C : 0;
     const int Cin = xa.C + Cb;
     bf16* h0 = alloc(static_cast<size_t>(M) * Cin);
-    groupnorm(xa.p, xa.C, xb, Cb, B, hw, m_.cfg_.norm_eps, r.n1, 1, h0);
-    bf16* h1 = alloc(static_cast<size_t>(M) * r.cout);
+    groupnorm(xa, xb, B, m_.cfg_.norm_eps, r.n1, 1, h0);
+    Act h1{alloc(static_cast<size_t>(M) * r.cout), r.cout, xa.H, xa.W, stats_alloc(B, r.cout, xa.H, xa.W)};
     {
       GemmDesc d;
       d.conv = 1; d.A = h0; d.n_img = B; d.H = xa.H; d.W = xa.W; d.Cin = Cin;
       d.Wt = r.c1.w; d.N = r.cout; d.bias = r.c1.b;
       d.rowvec = temb_all + r.temb_off; d.ld_rowvec = ld_temb;
-      d.out = h1; d.ldo = r.cout;
+      d.out = h1.p; d.ldo = r.cout;
+      d.stats = h1.stats;
       gemm(d);
     }
     release(h0);
     bf16* h2 = alloc(static_cast<size_t>(M) * r.cout);
-    groupnorm(h1, r.cout, nullptr, 0, B, hw, m_.cfg_.norm_eps, r.n2, 1, h2);
-    release(h1);
+    groupnorm(h1, nullptr, B, m_.cfg_.norm_eps, r.n2, 1, h2);
+    release(h1.p);
     const bf16* res = xa.p;
     bf16* sc = nullptr;
     if (r.sc.w) {
       sc = alloc(static_cast<size_t>(M) * r.cout);
       GemmDesc d;
       d.A = xa.p; d.lda = xa.C; d.K1 = xa.C;
-      if (xb) { d.A2 = xb; d.lda2 = Cb; d.K2 = Cb; }
+      if (xb) { d.A2 = xb->p; d.lda2 = Cb; d.K2 = Cb; }
       d.Wt = r.sc.w; d.M = M; d.N = r.cout; d.bias = r.sc.b; d.out = sc; d.ldo = r.cout;
       gemm(d);
       res = sc;
     }
-    bf16* out = alloc(static_cast<size_t>(M) * r.cout);
+    Act out{alloc(static_cast<size_t>(M) * r.cout), r.cout, xa.H, xa.W, stats_alloc(B, r.cout, xa.H, xa.W)};
     {
       GemmDesc d;
       d.conv = 1; d.A = h2; d.n_img = B; d.H = xa.H; d.W = xa.W; d.Cin = r.cout;
       d.Wt = r.c2.w; d.N = r.cout; d.bias = r.c2.b;
       d.residual = res; d.ld_res = r.cout;
-      d.out = out; d.ldo = r.cout;
+      d.out = out.p; d.ldo = r.cout;
+      d.stats = out.stats;
       gemm(d);
     }
     release(h2);
     if (sc) release(sc);
-    return {out, r.cout, xa.H, xa.W};
+    return out;
   }
 
   // Frame-sharded 3-D attention: the QKV GEMM epilogue stores its K|V columns straight into every rank's gathered
@@ -691,7 +722,7 @@ class PlanBuilder {
   Act transformer(const XfW& x, Act in, int num_frames) {
     const int B = p_.B, hw = in.H * in.W, M = B * hw, C = x.C;
     bf16* n = alloc(static_cast<size_t>(M) * C);
-    groupnorm(in.p, C, nullptr, 0, B, hw, 1e-6f, x.gn, 0, n);
+    groupnorm(in, nullptr, B, 1e-6f, x.gn, 0, n);
     bf16* t = alloc(static_cast<size_t>(M) * C);
     {
       GemmDesc d;
@@ -728,26 +759,28 @@ class PlanBuilder {
     }
     release(g);
     release(t1);
-    bf16* out = alloc(static_cast<size_t>(M) * C);
+    Act out{alloc(static_cast<size_t>(M) * C), C, in.H, in.W, stats_alloc(B, C, in.H, in.W)};
     {
       GemmDesc d;
       d.A = t3; d.lda = C; d.K1 = C; d.Wt = x.pout.w; d.M = M; d.N = C; d.bias = x.pout.b;
-      d.residual = in.p; d.ld_res = C; d.out = out; d.ldo = C;
+      d.residual = in.p; d.ld_res = C; d.out = out.p; d.ldo = C;
+      d.stats = out.stats; d.stats_rows = hw;
       gemm(d);
     }
     release(t3);
-    return {out, C, in.H, in.W};
+    return out;
   }
 
-  Act conv3x3(const LinW& w, Act in, int act = 0, int n_img = 0) {
+  Act conv3x3(const LinW& w, Act in, int act = 0, int n_img = 0, bool want_stats = false) {
     if (n_img <= 0) n_img = p_.B;
     const int M = n_img * in.H * in.W;
-    bf16* out = alloc(static_cast<size_t>(M) * w.out);
+    Act out{alloc(static_cast<size_t>(M) * w.out), w.out, in.H, in.W, want_stats ? stats_alloc(n_img, w.out, in.H, in.W) : nullptr};
     GemmDesc d;
     d.conv = 1; d.A = in.p; d.n_img = n_img; d.H = in.H; d.W = in.W; d.Cin = in.C;
-    d.Wt = w.w; d.N = w.out; d.bias = w.b; d.out = out; d.ldo = w.out; d.act = act;
+    d.Wt = w.w; d.N = w.out; d.bias = w.b; d.out = out.p; d.ldo = w.out; d.act = act;
+    d.stats = out.stats;
     gemm(d);
-    return {out, w.out, in.H, in.W};
+    return out;
   }
 
   int build() {
@@ -759,10 +792,19 @@ class PlanBuilder {
     const int C0 = ch[0], TE = 4 * C0, L = cfg.layers_per_block;
     const int M0 = B * h * w;
 
-    {
+    {  // scratch of the stand-alone GroupNorm statistics kernel (small shapes only)
       const size_t fl = groupnorm_scratch_floats(B, cfg.norm_num_groups);
       gn_partials_ = reinterpret_cast<float*>(alloc(fl * 2));
       if (!dry_ && cudaMemset(gn_partials_, 0, fl * sizeof(float)) != cudaSuccess) rc_ = 2;
+    }
+    if (!dry_ && p_.stats_words > 0) {  // GroupNorm statistics pool (size from the dry run): zeroed once per forward
+      stats_pool_ = reinterpret_cast<long long*>(alloc(p_.stats_words * 4));
+      long long* pool = stats_pool_;
+      const size_t bytes = p_.stats_words * sizeof(long long);
+      op([=](cudaStream_t s) {
+        D4D_CUDA_OK(cudaMemsetAsync(pool, 0, bytes, s));
+        return 0;
+      });
     }
 
     // ---- 1. time (+ frame-index) embedding: UNET:519-546 ----
@@ -879,14 +921,16 @@ class PlanBuilder {
       bf16* col = alloc(static_cast<size_t>(M0) * KP);
       op([=](cudaStream_t s) { return im2col_nchw_run(pl->sample, B, Cin, h, w, cp, KP, col, s); });
       bf16* x0 = alloc(static_cast<size_t>(M0) * C0);
+      long long* st0 = stats_alloc(B, C0, h, w);
       GemmDesc d;
       d.A = col; d.lda = KP; d.K1 = KP; d.Wt = m.conv_in_.w; d.M = M0; d.N = C0; d.bias = m.conv_in_.b;
       if (pose_emb) { d.residual = pose_emb; d.ld_res = C0; }
       d.out = x0; d.ldo = C0;
+      d.stats = st0; d.stats_rows = h * w;
       gemm(d);
       release(col);
       if (pose_emb) release(pose_emb);
-      x = {x0, C0, h, w};
+      x = {x0, C0, h, w, st0};
     }
     tap("conv_in", x);
 
@@ -896,7 +940,7 @@ class PlanBuilder {
     for (int i = 0; i < 4; ++i) {
       const int nf = (4 - i - 1) < cfg.num_3d_attn_blocks ? F : 1;
       for (int j = 0; j < L; ++j) {
-        Act y = resnet(m.down_res_[i][j], x, nullptr, 0, temb_all, ldt);
+        Act y = resnet(m.down_res_[i][j], x, nullptr, temb_all, ldt);
         if (i < 3) {
           Act z = transformer(m.down_xf_[i][j], y, nf);
           release(y.p);
@@ -911,21 +955,23 @@ class PlanBuilder {
         const Act xi = x;
         op([=](cudaStream_t s) { return im2col_nhwc_run(xi.p, B, xi.H, xi.W, xi.C, 3, 2, col, s); });
         bf16* y = alloc(static_cast<size_t>(Mo) * x.C);
+        long long* sty = stats_alloc(B, x.C, Ho, Wo);
         GemmDesc d;
         d.A = col; d.lda = 9 * x.C; d.K1 = 9 * x.C; d.Wt = m.down_ds_[i].w; d.M = Mo; d.N = x.C; d.bias = m.down_ds_[i].b; d.out = y; d.ldo = x.C;
+        d.stats = sty; d.stats_rows = Ho * Wo;
         gemm(d);
         release(col);
-        x = {y, x.C, Ho, Wo};
+        x = {y, x.C, Ho, Wo, sty};
         skips.push_back(x);
       }
       tap("down_blocks." + std::to_string(i), x);
     }
     // ---- 4. mid: UNET:568-572 ----
     {
-      Act y = resnet(m.mid_res_[0], x, nullptr, 0, temb_all, ldt);  // x is a skip: keep it
+      Act y = resnet(m.mid_res_[0], x, nullptr, temb_all, ldt);  // x is a skip: keep it
       Act z = transformer(m.mid_xf_, y, F);
       release(y.p);
-      Act u = resnet(m.mid_res_[1], z, nullptr, 0, temb_all, ldt);
+      Act u = resnet(m.mid_res_[1], z, nullptr, temb_all, ldt);
       release(z.p);
       x = u;
     }
@@ -936,7 +982,7 @@ class PlanBuilder {
       for (int j = 0; j <= L; ++j) {
         const Act sk = skips.back();
         skips.pop_back();
-        Act y = resnet(m.up_res_[i][j], x, sk.p, sk.C, temb_all, ldt);
+        Act y = resnet(m.up_res_[i][j], x, &sk, temb_all, ldt);
         release(x.p);
         release(sk.p);
         if (i > 0) {
@@ -952,7 +998,7 @@ class PlanBuilder {
         op([=](cudaStream_t s) { return upsample2x_run(xi.p, B, xi.H, xi.W, xi.C, up, s); });
         release(x.p);
         Act ua{up, x.C, 2 * x.H, 2 * x.W};
-        Act y = conv3x3(m.up_us_[i], ua);
+        Act y = conv3x3(m.up_us_[i], ua, 0, 0, true);
         release(up);
         x = y;
       }
@@ -961,7 +1007,7 @@ class PlanBuilder {
     // ---- 6. out: UNET:590-593 ----
     {
       bf16* n = alloc(static_cast<size_t>(M0) * C0);
-      groupnorm(x.p, C0, nullptr, 0, B, h * w, cfg.norm_eps, m.norm_out_, 1, n);
+      groupnorm(x, nullptr, B, cfg.norm_eps, m.norm_out_, 1, n);
       release(x.p);
       Act na{n, C0, h, w};
       Act y = conv3x3(m.conv_out_, na);
@@ -984,6 +1030,8 @@ class PlanBuilder {
   std::vector<std::pair<size_t, size_t>> free_;
   std::map<size_t, size_t> live_;
   float* gn_partials_ = nullptr;
+  long long* stats_pool_ = nullptr;
+  size_t stats_used_ = 0;
   int rc_ = 0;
 };
 
@@ -1035,6 +1083,8 @@ int Model::get_plan(const int* domain_ids, int n_domains, int B, int F, int h, i
     PlanBuilder dry(*this, scratch, true, nullptr);
     if (int rc = dry.build()) return rc;
     peak = dry.peak();
+    p->stats_words = dry.stats_words();
+    peak += (p->stats_words * sizeof(long long) + 255) & ~size_t(255);
   }
   D4D_CUDA_OK(cudaMalloc(&p->arena, peak + 1024));
   p->arena_bytes = peak;
@@ -1168,7 +1218,7 @@ int Model::profile(const bf16* sample, const long long* timestep, const bf16* sk
     D4D_CUDA_OK(cudaEventElapsedTime(&ms, p->events[i], p->events[i + 1]));
     const int k = p->op_kind[i];
     ms_by_kind[k] += ms;
-    launches_by_kind[k] += (k == 3 ? 2 : 1);
+    launches_by_kind[k] += 1;
     flops_by_kind[k] += p->op_flops[i];
   }
   return 0;

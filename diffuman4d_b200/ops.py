@@ -110,6 +110,21 @@ def groupnorm(x1: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, groups:
     return out
 
 
+def conv3x3_groupnorm(x_nhwc: torch.Tensor, w_octi: torch.Tensor, bias: Optional[torch.Tensor], gamma: torch.Tensor,
+                      beta: torch.Tensor, groups: int, eps: float, silu: bool, residual: Optional[torch.Tensor] = None):
+    """conv3x3 whose epilogue accumulates the GroupNorm statistics of its output + the GroupNorm(+SiLU) that consumes them
+    (no statistics pass).  Returns (conv_out, gn_out), both [n, H, W, Cout]."""
+    _bf16c(x_nhwc, "x"), _bf16c(w_octi, "w")
+    n, H, W, Cin = x_nhwc.shape
+    Cout = w_octi.shape[0]
+    conv_out = torch.empty(n, H, W, Cout, device=x_nhwc.device, dtype=torch.bfloat16)
+    gn_out = torch.empty_like(conv_out)
+    check(lib().d4d_op_conv3x3_groupnorm(_p(x_nhwc), n, H, W, Cin, _p(w_octi), Cout, _p(bias), _p(residual), groups,
+                                         float(eps), _p(gamma), _p(beta), int(silu), _p(conv_out), _p(gn_out), _stream()),
+          "d4d_op_conv3x3_groupnorm")
+    return conv_out, gn_out
+
+
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
     _bf16c(x, "x")
     rows, C = x.shape

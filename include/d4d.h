@@ -135,6 +135,12 @@ int d4d_op_attention(const void* q, const void* k, const void* v, int ld_qkv, vo
                      int seq, int heads, int head_dim, float scale, void* stream);
 int d4d_op_groupnorm(const void* x1, int C1, const void* x2, int C2, int n_img, int hw, int groups, float eps,
                      const float* gamma, const float* beta, int silu, void* out, void* stream);
+/* conv3x3 (+bias, +residual) whose epilogue accumulates the per-(image, channel) sums of its output, followed by the
+ * GroupNorm(+SiLU) that reads those sums instead of running a statistics pass: the pair every ResnetBlock2D of the UNet
+ * executes (needs H*W % 32 == 0).  conv_out [n,H,W,Cout] and gn_out [n,H,W,Cout] are both written. */
+int d4d_op_conv3x3_groupnorm(const void* x_nhwc, int n_img, int H, int W, int Cin, const void* Wt, int Cout,
+                             const float* bias, const void* residual, int groups, float eps, const float* gamma,
+                             const float* beta, int silu, void* conv_out, void* gn_out, void* stream);
 int d4d_op_layernorm(const void* x, int rows, int C, float eps, const float* gamma, const float* beta, void* out,
                      void* stream);
 /* Debug tap (per-level drift reports in tests/): runs the forward of d4d_unet_forward up to intermediate activation

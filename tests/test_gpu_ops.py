@@ -175,6 +175,28 @@ def test_groupnorm(cuda, n, hw, C1, C2, silu, eps):
     _close(out, ref)
 
 
+@pytest.mark.parametrize("n,H,W,Cin,Cout,silu", [(2, 16, 16, 64, 64, True), (3, 8, 8, 320, 640, True), (2, 32, 32, 320, 320, False),
+                                                 (2, 16, 24, 128, 256, True), (1, 64, 64, 320, 320, True)])
+def test_conv3x3_fused_groupnorm_stats(cuda, n, H, W, Cin, Cout, silu):
+    """conv epilogue accumulates per-(image, channel) sums; GroupNorm applies from them (the resnet pair of the UNet plan)."""
+    from diffuman4d_b200 import ops
+    g = torch.Generator().manual_seed(75)
+    x = _rand((n, H, W, Cin), 71)
+    w = _rand((Cout, Cin, 3, 3), 72, std=(9 * Cin) ** -0.5)
+    bias = (torch.randn(Cout, generator=g) + 1.5).cuda()   # a mean well away from zero: E[x^2] - E[x]^2 must hold up
+    res = _rand((n, H, W, Cout), 73)
+    gamma = (1 + 0.2 * torch.randn(Cout, generator=g)).cuda()
+    beta = (0.1 * torch.randn(Cout, generator=g)).cuda()
+    conv_out, gn_out = ops.conv3x3_groupnorm(x, ops.conv_weight_to_octi(w), bias, gamma, beta, 32, 1e-5, silu, residual=res)
+    ref_conv = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), bias, padding=1).permute(0, 2, 3, 1) + res.float()
+    _close(conv_out, ref_conv)
+    # GroupNorm reference on the bf16 tensor the kernel actually stored (what the next layer of the reference sees)
+    ref = F.group_norm(conv_out.float().permute(0, 3, 1, 2), 32, gamma, beta, 1e-5).permute(0, 2, 3, 1)
+    if silu:
+        ref = F.silu(ref)
+    _close(gn_out, ref)
+
+
 @pytest.mark.parametrize("rows,C", [(100, 64), (4096, 320), (1000, 640), (77, 1280)])
 def test_layernorm(cuda, rows, C):
     from diffuman4d_b200 import ops

@@ -267,7 +267,7 @@ def test_full_size_properties(cuda):
     x2[F:] = torch.randn_like(x2[F:])
     y2 = unet(x2, t, sk, doms, F, return_dict=False)[0]
     assert torch.equal(y2[:F], y[:F])                                            # negative half untouched
-    assert unet.forward_launches(2, 2 * F, F, h, w) > 300
+    assert unet.forward_launches(2, 2 * F, F, h, w) > 250     # (61 GroupNorm statistics launches are fused away)
     # temporal window W24 (12 cond + 12 target frames => 48 images): finite, deterministic, and different from 'spatial'
     F = 24
     x, t, sk = _inputs(cfg, F, h, w, seed=3)
