@@ -38,9 +38,10 @@ void set_error(const std::string& msg);          // thread-local last error (d4d
 // 2-D row-major bf16 matrix [rows, cols] with leading dimension ld (elements); box = {box_cols, box_rows}.
 int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
                  uint32_t box_cols, uint32_t box_rows, int swizzle_bytes);
-// 4-D NHWC bf16 tensor [n, h, w, c]; box = {box_c, box_w, box_h, box_n}.
+// 4-D NHWC bf16 tensor [n, h, w, c]; box = {box_c, box_w, box_h, box_n} ELEMENTS LOADED; `stride` > 1 loads every
+// stride-th pixel along w and h (elementStrides: the box then spans stride * box_w x stride * box_h pixels).
 int make_tmap_nhwc(CUtensorMap* out, const void* base, uint64_t n, uint64_t h, uint64_t w, uint64_t c,
-                   uint32_t box_c, uint32_t box_w, uint32_t box_h, uint32_t box_n, int swizzle_bytes);
+                   uint32_t box_c, uint32_t box_w, uint32_t box_h, uint32_t box_n, int swizzle_bytes, int stride = 1);
 
 #ifdef __CUDACC__
 // ------------------------------------------------------------------------------------------

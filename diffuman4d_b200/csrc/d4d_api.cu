@@ -289,6 +289,21 @@ int d4d_op_groupnorm(const void* x1, int C1, const void* x2, int C2, int n_img, 
   D4D_API_END
 }
 
+int d4d_op_conv_resample(const void* x_nhwc, int n_img, int H, int W, int Cin, const void* Wt, int Cout, const float* bias,
+                         int kind, int up_a, int up_b, void* out, void* stream) {
+  D4D_API_BEGIN
+  D4D_REQUIRE(n_img > 0 && H > 0 && W > 0 && kind >= 1 && kind <= 3, "conv_resample arguments");
+  d4d::GemmDesc d;
+  d.conv = 1; d.conv_kind = kind; d.up_a = up_a; d.up_b = up_b;
+  d.A = static_cast<const bf16*>(x_nhwc); d.n_img = n_img; d.H = H; d.W = W; d.Cin = Cin;
+  d.Wt = static_cast<const bf16*>(Wt); d.N = Cout; d.bias = bias;
+  d.out = static_cast<bf16*>(out); d.ldo = Cout;
+  d4d::GemmLaunch L;
+  if (int rc = d4d::gemm_prepare(d, &L)) return rc;
+  return d4d::gemm_run(L, static_cast<cudaStream_t>(stream));
+  D4D_API_END
+}
+
 int d4d_op_conv3x3_groupnorm(const void* x_nhwc, int n_img, int H, int W, int Cin, const void* Wt, int Cout, const float* bias,
                              const void* residual, int groups, float eps, const float* gamma, const float* beta, int silu,
                              void* conv_out, void* gn_out, void* stream) {

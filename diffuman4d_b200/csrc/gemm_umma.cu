@@ -52,13 +52,19 @@ constexpr int ACC_STRIDE = 256;
 struct TileCoord {
   int m0;          // plain: first row.  conv: unused
   int n_img0, y0, x0;
+  int pa, pb;      // conv, n_phases == 4: sub-pixel phase of this tile (0 otherwise)
 };
 
 __device__ __forceinline__ void tile_coords(const GemmKernelArgs& a, int m_tile, TileCoord& t) {
   if (a.mode == 0) {
     t.m0 = m_tile * BLOCK_M;
     t.n_img0 = t.y0 = t.x0 = 0;
+    t.pa = t.pb = 0;
   } else {
+    const int ph = a.n_phases > 1 ? m_tile / a.tiles_per_phase : 0;  // phases outermost: concurrent CTAs share a weight slab
+    m_tile -= ph * a.tiles_per_phase;
+    t.pa = ph >> 1;
+    t.pb = ph & 1;
     int tx = m_tile % a.tiles_x;
     int r = m_tile / a.tiles_x;
     int ty = r % a.tiles_y;
@@ -186,11 +192,11 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         } else {
           const int tap = kb / a.cin_blocks;
           const int cb = kb - tap * a.cin_blocks;
-          const int ky = tap / 3, kx = tap - ky * 3;
           if (elect_one()) {
             mbar_expect_tx(&full[stage], A_BYTES + b_bytes);
-            tma_load_4d(sa, &tmap_a, &full[stage], cb * BLOCK_K, tc.x0 + kx - 1, tc.y0 + ky - 1, tc.n_img0);
-            tma_load_2d(sb, &tmap_b, &full[stage], tap * a.Cin + cb * BLOCK_K, n0);
+            tma_load_4d(sa, &tmap_a, &full[stage], cb * BLOCK_K, tc.x0 * a.in_stride + a.tap_dx[tap] + tc.pb,
+                        tc.y0 * a.in_stride + a.tap_dy[tap] + tc.pa, tc.n_img0);
+            tma_load_2d(sb, &tmap_b, &full[stage], tap * a.Cin + cb * BLOCK_K, n0 + (tc.pa * 2 + tc.pb) * a.N);
           }
         }
         __syncwarp();
@@ -263,7 +269,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const int bn = r2 / a.BH;
         const int x = tc.x0 + bx, y = tc.y0 + by, n = tc.n_img0 + bn;
         valid = (x < a.W) && (y < a.H) && (n < a.n_img);
-        row = (static_cast<long long>(n) * a.H + y) * a.W + x;
+        row = (static_cast<long long>(n) * a.out_H + (y * a.out_sy + a.out_oy + tc.pa)) * a.out_W + (x * a.out_sx + a.out_ox + tc.pb);
         img = n;
       }
     };
@@ -578,27 +584,55 @@ int gemm_prepare(const GemmDesc& d, GemmLaunch* L) {
     if (int rc = make_tmap_2d(&L->tmap_b, d.Wt, d.N, K, K, BLOCK_K, bn, 128)) return rc;
   } else {
     D4D_REQUIRE(d.Cin % 8 == 0, "conv Cin must be a multiple of 8");
+    D4D_REQUIRE(d.conv_kind >= 0 && d.conv_kind <= 3, "conv_kind");
+    D4D_REQUIRE(d.conv_kind != 1 || (d.H % 2 == 0 && d.W % 2 == 0), "stride-2 conv needs even H, W");
     a.mode = 1;
-    a.H = d.H; a.W = d.W; a.n_img = d.n_img; a.Cin = d.Cin;
-    a.M = d.n_img * d.H * d.W;
+    a.n_img = d.n_img; a.Cin = d.Cin;
+    // tap table, grid of output positions, output pixel mapping (GemmKernelArgs)
+    a.in_stride = 1; a.out_sy = a.out_sx = 1; a.out_oy = a.out_ox = 0;
+    a.n_phases = 1;
+    if (d.conv_kind >= 2) {  // sub-pixel phase (a, b): rows {-1, 0} for a = 0, {0, +1} for a = 1 (same for columns)
+      const int pa = d.conv_kind == 3 ? 0 : d.up_a, pb = d.conv_kind == 3 ? 0 : d.up_b;  // kind 3: the tile adds its phase
+      a.n_taps = 4;
+      for (int t = 0; t < 4; ++t) {
+        a.tap_dy[t] = static_cast<signed char>((t >> 1) + pa - 1);
+        a.tap_dx[t] = static_cast<signed char>((t & 1) + pb - 1);
+      }
+      a.H = d.H; a.W = d.W; a.out_H = 2 * d.H; a.out_W = 2 * d.W;
+      a.out_sy = a.out_sx = 2; a.out_oy = pa; a.out_ox = pb;
+      if (d.conv_kind == 3) a.n_phases = 4;
+    } else {
+      a.n_taps = 9;
+      for (int t = 0; t < 9; ++t) {
+        a.tap_dy[t] = static_cast<signed char>(t / 3 - 1);
+        a.tap_dx[t] = static_cast<signed char>(t % 3 - 1);
+      }
+      if (d.conv_kind == 1) { a.in_stride = 2; a.H = d.H / 2; a.W = d.W / 2; }
+      else { a.H = d.H; a.W = d.W; }
+      a.out_H = a.H; a.out_W = a.W;
+    }
+    a.M = d.n_img * a.H * a.W;
     a.cin_blocks = (d.Cin + BLOCK_K - 1) / BLOCK_K;
-    a.k_blocks = 9 * a.cin_blocks;
+    a.k_blocks = a.n_taps * a.cin_blocks;
     a.kb_split = a.k_blocks;
-    // spatial tile: BW x BH x BN = 128 output pixels
-    int bw = 16; while (bw > d.W) bw >>= 1;
-    int bh = 128 / bw; while (bh > d.H && bh > 1) bh >>= 1;
+    // spatial tile: BW x BH x BN = 128 output positions
+    int bw = 16; while (bw > a.W) bw >>= 1;
+    int bh = 128 / bw; while (bh > a.H && bh > 1) bh >>= 1;
     // H, W need not be powers of two: the tile may overhang, TMA zero-fills and the epilogue masks
     int bnimg = 128 / (bw * bh);
     D4D_REQUIRE(bw * bh * bnimg == 128 && bnimg <= 256, "conv tile shape");
     D4D_REQUIRE(d.stats == nullptr || (bw * bh) % 32 == 0, "statistics need 32-row warps inside one image");
     a.BW = bw; a.BH = bh; a.BN = bnimg;
-    a.tiles_x = (d.W + bw - 1) / bw;
-    a.tiles_y = (d.H + bh - 1) / bh;
+    a.tiles_x = (a.W + bw - 1) / bw;
+    a.tiles_y = (a.H + bh - 1) / bh;
     const int tiles_n = (d.n_img + bnimg - 1) / bnimg;
-    a.m_tiles = a.tiles_x * a.tiles_y * tiles_n;
-    if (int rc = make_tmap_nhwc(&L->tmap_a, d.A, d.n_img, d.H, d.W, d.Cin, BLOCK_K, bw, bh, bnimg, 128)) return rc;
+    a.tiles_per_phase = a.tiles_x * a.tiles_y * tiles_n;
+    a.m_tiles = a.tiles_per_phase * a.n_phases;
+    a.M *= a.n_phases;  // output positions of the launch (FLOP count)
+    if (int rc = make_tmap_nhwc(&L->tmap_a, d.A, d.n_img, d.H, d.W, d.Cin, BLOCK_K, bw, bh, bnimg, 128, a.in_stride)) return rc;
     L->tmap_a2 = L->tmap_a;
-    if (int rc = make_tmap_2d(&L->tmap_b, d.Wt, d.N, 9ull * d.Cin, 9ull * d.Cin, BLOCK_K, bn, 128)) return rc;
+    const uint64_t kw = static_cast<uint64_t>(a.n_taps) * d.Cin;
+    if (int rc = make_tmap_2d(&L->tmap_b, d.Wt, static_cast<uint64_t>(d.N) * a.n_phases, kw, kw, BLOCK_K, bn, 128)) return rc;
   }
   int dev = 0, sms = 0;
   D4D_CUDA_OK(cudaGetDevice(&dev));

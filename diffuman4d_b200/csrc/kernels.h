@@ -21,9 +21,17 @@ constexpr float kGnSqScale = 16777216.f;    // 2^24
 struct GemmKernelArgs {
   int dbg;  // ablation switches (tools/ablate_gemm.py); 0 in production
   int M, N, k_blocks, block_n, n_tiles, m_tiles;
-  int mode;      // 0 plain, 1 conv3x3 (stride 1, pad 1, NHWC)
+  int mode;      // 0 plain, 1 implicit-GEMM convolution over NHWC (tap table below; TMA zero fill = padding)
   int kb_split;  // plain: k-blocks served by A (rest by A2)
-  int H, W, n_img, Cin, cin_blocks, BW, BH, BN, tiles_x, tiles_y;
+  int H, W, n_img, Cin, cin_blocks, BW, BH, BN, tiles_x, tiles_y;  // H, W: the grid of output positions the tiles walk
+  // conv: tap t reads input pixel (y * in_stride + tap_dy[t], x * in_stride + tap_dx[t]) for output position (y, x); the
+  // result goes to output pixel (y * out_sy + out_oy, x * out_sx + out_ox) of an [n_img, out_H, out_W, ldo] tensor.
+  //   3x3 / pad 1:            9 taps (-1..1), strides 1
+  //   3x3 / stride 2 / pad 1: 9 taps (-1..1), in_stride 2 (the tensor map skips every other pixel)   [Downsample2D]
+  //   nearest x2 + 3x3:       four 2x2 sub-pixel phases on the LOW-resolution input, out stride 2     [Upsample2D]
+  int n_taps, in_stride, out_sy, out_sx, out_oy, out_ox, out_H, out_W;
+  int n_phases, tiles_per_phase;  // 4: all sub-pixel phases in ONE launch (phase = m_tile / tiles_per_phase; weights [4][N][4][Cin])
+  signed char tap_dy[9], tap_dx[9];
   const float* bias;  // [N] fp32 or null
   const bf16* rowvec; // [images, ld_rowvec] bf16 or null (added to every row of image row/rows_per_image)
   int ld_rowvec, rows_per_image;
@@ -73,8 +81,13 @@ struct GemmDesc {
   int kv_world = 0, kv_col0 = 0, kv_ld = 0;
   long long kv_rows_local = 0, kv_rows_global = 0, kv_row_offset = 0;
   bf16* kv_dst[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-  // conv3x3: A is NHWC [n_img, H, W, Cin]
+  // conv: A is NHWC [n_img, H, W, Cin]; Wt [N][taps][Cin]
   int conv = 0, n_img = 0, H = 0, W = 0, Cin = 0;
+  // conv_kind: 0 = 3x3 stride 1 pad 1 (output H x W);  1 = 3x3 stride 2 pad 1 (output H/2 x W/2);
+  //            2 = one sub-pixel phase (up_a, up_b) of "nearest x2 upsample, then 3x3 pad 1": 4 taps on the H x W input with
+  //                pre-summed weights (Wt [N][4][Cin]), written to pixels (2y + up_a, 2x + up_b) of the 2H x 2W output
+  //            3 = all four phases in one launch (Wt [4 phases = a*2+b][N][4][Cin]): 4x the tiles, no wave quantisation per phase
+  int conv_kind = 0, up_a = 0, up_b = 0;
 };
 
 struct GemmLaunch {

@@ -189,28 +189,49 @@ __global__ void __launch_bounds__(GN_MAX_THREADS, 2) gn_apply_kernel(const GnArg
     for (int g = threadIdx.x; g < 2 * a.groups; g += blockDim.x)
       sm[(g & 1) * a.groups + (g >> 1)] = a.final_stats[static_cast<size_t>(img) * a.groups * 2 + g];
   } else {
-    // one warp per group: sum the group's channels' {sum, sumsq} (the virtual concat may straddle the two sources)
+    // one warp per group, up to 4 groups per warp side by side (their load / shuffle chains are independent, so the
+    // latencies overlap); the channel totals are summed as integers (exact), the butterfly runs on doubles in a fixed order
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    for (int g = warp < nwarps ? warp : a.groups; g < a.groups; g += nwarps) {  // (a trailing partial warp sits out)
-      long long s = 0, q = 0;  // exact integer sums of the fixed-point channel totals
-      for (int i = lane; i < a.cpg; i += 32) {
-        const int c = g * a.cpg + i;
-        const longlong2 v = c < a.C1 ? __ldcg(reinterpret_cast<const longlong2*>(a.ch_stats1) + static_cast<size_t>(img) * a.C1 + c)
-                                     : __ldcg(reinterpret_cast<const longlong2*>(a.ch_stats2) + static_cast<size_t>(img) * a.C2 + (c - a.C1));
-        s += v.x;
-        q += v.y;
-      }
+    if (warp < nwarps) {  // (a trailing partial warp sits out)
+      for (int g0 = warp; g0 < a.groups; g0 += 4 * nwarps) {
+        double ds[4], dq[4];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        s += __shfl_xor_sync(0xffffffffu, s, o);
-        q += __shfl_xor_sync(0xffffffffu, q, o);
-      }
-      if (lane == 0) {  // 32 groups per CTA: double precision keeps E[x^2] - mean^2 exact up to the fixed-point resolution
-        const double inv_n = 1.0 / (static_cast<double>(a.cpg) * static_cast<double>(a.hw));
-        const double mean = static_cast<double>(s) * (1.0 / static_cast<double>(kGnSumScale)) * inv_n;
-        const double var = fmax(static_cast<double>(q) * (1.0 / static_cast<double>(kGnSqScale)) * inv_n - mean * mean, 0.0);
-        sm[g] = static_cast<float>(mean);
-        sm[a.groups + g] = rsqrtf(static_cast<float>(var) + a.eps);
+        for (int u = 0; u < 4; ++u) {
+          const int g = g0 + u * nwarps;
+          long long s = 0, q = 0;
+          if (g < a.groups) {
+            for (int i = lane; i < a.cpg; i += 32) {  // (the virtual concat may straddle the two sources)
+              const int c = g * a.cpg + i;
+              const longlong2 v = c < a.C1 ? __ldcg(reinterpret_cast<const longlong2*>(a.ch_stats1) + static_cast<size_t>(img) * a.C1 + c)
+                                           : __ldcg(reinterpret_cast<const longlong2*>(a.ch_stats2) + static_cast<size_t>(img) * a.C2 + (c - a.C1));
+              s += v.x;
+              q += v.y;
+            }
+          }
+          ds[u] = static_cast<double>(s);
+          dq[u] = static_cast<double>(q);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            ds[u] += __shfl_xor_sync(0xffffffffu, ds[u], o);
+            dq[u] += __shfl_xor_sync(0xffffffffu, dq[u], o);
+          }
+        }
+        if (lane < 4) {
+          const int g = g0 + lane * nwarps;
+          if (g < a.groups) {
+            const double s = lane == 0 ? ds[0] : (lane == 1 ? ds[1] : (lane == 2 ? ds[2] : ds[3]));
+            const double q = lane == 0 ? dq[0] : (lane == 1 ? dq[1] : (lane == 2 ? dq[2] : dq[3]));
+            // double precision keeps E[x^2] - mean^2 exact up to the fixed-point resolution
+            const double inv_n = 1.0 / (static_cast<double>(a.cpg) * static_cast<double>(a.hw));
+            const double mean = s * (1.0 / static_cast<double>(kGnSumScale)) * inv_n;
+            const double var = fmax(q * (1.0 / static_cast<double>(kGnSqScale)) * inv_n - mean * mean, 0.0);
+            sm[g] = static_cast<float>(mean);
+            sm[a.groups + g] = rsqrtf(static_cast<float>(var) + a.eps);
+          }
+        }
       }
     }
   }

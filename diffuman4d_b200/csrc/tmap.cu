@@ -60,7 +60,7 @@ int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t col
 }
 
 int make_tmap_nhwc(CUtensorMap* out, const void* base, uint64_t n, uint64_t h, uint64_t w, uint64_t c, uint32_t box_c,
-                   uint32_t box_w, uint32_t box_h, uint32_t box_n, int swizzle_bytes) {
+                   uint32_t box_w, uint32_t box_h, uint32_t box_n, int swizzle_bytes, int stride) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
@@ -70,8 +70,11 @@ int make_tmap_nhwc(CUtensorMap* out, const void* base, uint64_t n, uint64_t h, u
   D4D_REQUIRE((c * 2) % 16 == 0, "NHWC channel count must be a multiple of 8");
   cuuint64_t gdim[4] = {c, w, h, n};
   cuuint64_t gstr[3] = {c * 2, w * c * 2, h * w * c * 2};
-  cuuint32_t box[4] = {box_c, box_w, box_h, box_n};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
+  D4D_REQUIRE(stride >= 1 && stride <= 8 && box_w * stride <= 256 && box_h * stride <= 256, "TMA traversal stride");
+  // with elementStrides the box is given in tensor pixels and every stride-th one is loaded: ceil(box / stride) elements
+  const cuuint32_t s = static_cast<cuuint32_t>(stride);
+  cuuint32_t box[4] = {box_c, box_w * s, box_h * s, box_n};
+  cuuint32_t estr[4] = {1, s, s, 1};
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstr, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz(swizzle_bytes), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

@@ -445,7 +445,29 @@ int Model::finalize() {
       up_res_[i].push_back(resnetw(p + ".resnets." + std::to_string(j), rin + skip, cout));
       if (i > 0) up_xf_[i].push_back(xfw(p + ".attentions." + std::to_string(j), cout, cfg_.num_heads[3 - i], cfg_.has_attn2[3 - i] != 0));
     }
-    if (i < 3) up_us_[i] = convw(p + ".upsamplers.0.conv", cout, cout);
+    if (i < 3) {
+      // Upsample2D = nearest x2 followed by a 3x3 conv: every output pixel (2y + a, 2x + b) only ever sees a 2x2 patch of
+      // the LOW-resolution input, so the layer is computed as four sub-pixel phases with pre-summed weights
+      // (rows {-1, 0} weigh {w0, w1 + w2} for a = 0 and rows {0, +1} weigh {w0 + w1, w2} for a = 1; same for columns):
+      // 4/9 of the multiply-adds and no materialised upsampled tensor.  Layout per phase: [Cout][ty*2 + tx][Cin].
+      const auto& w = T(p + ".upsamplers.0.conv.weight");
+      std::vector<float> o(static_cast<size_t>(4) * cout * 4 * cout, 0.f);  // [phase = a*2+b][Cout][ty*2+tx][Cin]
+      for (int a = 0; a < 2; ++a)
+        for (int b = 0; b < 2; ++b)
+          for (int co = 0; co < cout; ++co)
+            for (int ci = 0; ci < cout; ++ci)
+              for (int ky = 0; ky < 3; ++ky)
+                for (int kx = 0; kx < 3; ++kx) {
+                  const int ty = a == 0 ? (ky == 0 ? 0 : 1) : (ky == 2 ? 1 : 0);
+                  const int tx = b == 0 ? (kx == 0 ? 0 : 1) : (kx == 2 ? 1 : 0);
+                  o[((static_cast<size_t>(a * 2 + b) * cout + co) * 4 + ty * 2 + tx) * cout + ci] +=
+                      w[(static_cast<size_t>(co) * cout + ci) * 9 + ky * 3 + kx];
+                }
+      up_us_[i].w = up_bf16(o);
+      up_us_[i].b = up_f32(T(p + ".upsamplers.0.conv.bias"));
+      up_us_[i].in = cout;
+      up_us_[i].out = cout;
+    }
   }
   norm_out_ = normw("conv_norm_out", C0);
   {
@@ -949,18 +971,15 @@ class PlanBuilder {
         x = y;
         skips.push_back(x);
       }
-      if (i < 3) {  // Downsample2D: 3x3 stride-2 pad-1 conv = im2col + GEMM
+      if (i < 3) {  // Downsample2D: 3x3 stride-2 pad-1 conv, read in place through a strided tensor map
         const int Ho = x.H / 2, Wo = x.W / 2, Mo = B * Ho * Wo;
-        bf16* col = alloc(static_cast<size_t>(Mo) * 9 * x.C);
-        const Act xi = x;
-        op([=](cudaStream_t s) { return im2col_nhwc_run(xi.p, B, xi.H, xi.W, xi.C, 3, 2, col, s); });
         bf16* y = alloc(static_cast<size_t>(Mo) * x.C);
         long long* sty = stats_alloc(B, x.C, Ho, Wo);
         GemmDesc d;
-        d.A = col; d.lda = 9 * x.C; d.K1 = 9 * x.C; d.Wt = m.down_ds_[i].w; d.M = Mo; d.N = x.C; d.bias = m.down_ds_[i].b; d.out = y; d.ldo = x.C;
-        d.stats = sty; d.stats_rows = Ho * Wo;
+        d.conv = 1; d.conv_kind = 1; d.A = x.p; d.n_img = B; d.H = x.H; d.W = x.W; d.Cin = x.C;
+        d.Wt = m.down_ds_[i].w; d.N = x.C; d.bias = m.down_ds_[i].b; d.out = y; d.ldo = x.C;
+        d.stats = sty;
         gemm(d);
-        release(col);
         x = {y, x.C, Ho, Wo, sty};
         skips.push_back(x);
       }
@@ -992,14 +1011,18 @@ class PlanBuilder {
         }
         x = y;
       }
-      if (i < 3) {  // Upsample2D: nearest x2 then 3x3 conv
-        bf16* up = alloc(static_cast<size_t>(B) * 4 * x.H * x.W * x.C);
-        const Act xi = x;
-        op([=](cudaStream_t s) { return upsample2x_run(xi.p, B, xi.H, xi.W, xi.C, up, s); });
+      if (i < 3) {  // Upsample2D (nearest x2, then 3x3 conv) as four sub-pixel phases on the low-resolution tensor
+        const int H2 = 2 * x.H, W2 = 2 * x.W;
+        Act y{alloc(static_cast<size_t>(B) * H2 * W2 * x.C), x.C, H2, W2, stats_alloc(B, x.C, x.H, x.W)};
+        {
+          GemmDesc d;
+          d.conv = 1; d.conv_kind = 3;
+          d.A = x.p; d.n_img = B; d.H = x.H; d.W = x.W; d.Cin = x.C;
+          d.Wt = m.up_us_[i].w; d.N = x.C; d.bias = m.up_us_[i].b; d.out = y.p; d.ldo = x.C;
+          d.stats = y.stats;
+          gemm(d);
+        }
         release(x.p);
-        Act ua{up, x.C, 2 * x.H, 2 * x.W};
-        Act y = conv3x3(m.up_us_[i], ua, 0, 0, true);
-        release(up);
         x = y;
       }
       tap("up_blocks." + std::to_string(i), x);

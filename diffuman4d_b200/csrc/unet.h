@@ -135,7 +135,8 @@ class Model {
   PoseW pose_;
   std::vector<ResnetW> down_res_[4], up_res_[4];
   std::vector<XfW> down_xf_[4], up_xf_[4];
-  LinW down_ds_[4], up_us_[4];
+  LinW down_ds_[4];
+  LinW up_us_[4];         // Upsample2D convs as four sub-pixel phase kernels: [phase = a*2+b][Cout][4][Cin] (unet.cu)
   ResnetW mid_res_[2];
   XfW mid_xf_;
   NormW norm_out_;

@@ -110,6 +110,54 @@ def groupnorm(x1: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, groups:
     return out
 
 
+def conv3x3_stride2(x_nhwc: torch.Tensor, w_octi: torch.Tensor, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """3x3 / stride 2 / pad 1 conv (Downsample2D) through a strided tensor map: [n,H,W,Cin] -> [n,H/2,W/2,Cout]."""
+    _bf16c(x_nhwc, "x"), _bf16c(w_octi, "w")
+    n, H, W, Cin = x_nhwc.shape
+    Cout = w_octi.shape[0]
+    out = torch.empty(n, H // 2, W // 2, Cout, device=x_nhwc.device, dtype=torch.bfloat16)
+    check(lib().d4d_op_conv_resample(_p(x_nhwc), n, H, W, Cin, _p(w_octi), Cout, _p(bias), 1, 0, 0, _p(out), _stream()),
+          "d4d_op_conv_resample")
+    return out
+
+
+def upsample_phase_weights(w_oihw: torch.Tensor):
+    """The four sub-pixel phase kernels [Cout, 4, Cin] (tap = ty*2+tx) of `nearest x2 -> conv3x3(w)`: output pixel
+    (2y+a, 2x+b) sees rows {-1, 0} with weights {w0, w1+w2} for a = 0 and rows {0, +1} with {w0+w1, w2} for a = 1 (columns
+    alike).  Same transform the C++ weight loader applies (csrc/unet.cu)."""
+    w = w_oihw.float()
+    rows = [[w[:, :, 0], w[:, :, 1] + w[:, :, 2]], [w[:, :, 0] + w[:, :, 1], w[:, :, 2]]]   # [a][ty] -> [Cout, Cin, 3(kx)]
+    out = []
+    for a in range(2):
+        for b in range(2):
+            taps = []
+            for ty in range(2):
+                r = rows[a][ty]
+                cols = [r[:, :, 0], r[:, :, 1] + r[:, :, 2]] if b == 0 else [r[:, :, 0] + r[:, :, 1], r[:, :, 2]]
+                taps += cols
+            out.append(torch.stack(taps, dim=1).to(torch.bfloat16).contiguous())      # [Cout, 4, Cin]
+    return out
+
+
+def upsample2x_conv3x3(x_nhwc: torch.Tensor, w_oihw: torch.Tensor, bias: Optional[torch.Tensor] = None,
+                       single_launch: bool = True) -> torch.Tensor:
+    """nearest x2 upsample followed by a 3x3 / pad 1 conv (Upsample2D) as four sub-pixel phases on the low-res input."""
+    _bf16c(x_nhwc, "x")
+    n, H, W, Cin = x_nhwc.shape
+    Cout = w_oihw.shape[0]
+    out = torch.empty(n, 2 * H, 2 * W, Cout, device=x_nhwc.device, dtype=torch.bfloat16)
+    phases = upsample_phase_weights(w_oihw)
+    if single_launch:
+        wp = torch.stack(phases).contiguous()                                          # [4, Cout, 4, Cin]
+        check(lib().d4d_op_conv_resample(_p(x_nhwc), n, H, W, Cin, _p(wp), Cout, _p(bias), 3, 0, 0, _p(out), _stream()),
+              "d4d_op_conv_resample")
+        return out
+    for ph, wp in enumerate(phases):
+        check(lib().d4d_op_conv_resample(_p(x_nhwc), n, H, W, Cin, _p(wp), Cout, _p(bias), 2, ph >> 1, ph & 1, _p(out),
+                                         _stream()), "d4d_op_conv_resample")
+    return out
+
+
 def conv3x3_groupnorm(x_nhwc: torch.Tensor, w_octi: torch.Tensor, bias: Optional[torch.Tensor], gamma: torch.Tensor,
                       beta: torch.Tensor, groups: int, eps: float, silu: bool, residual: Optional[torch.Tensor] = None):
     """conv3x3 whose epilogue accumulates the GroupNorm statistics of its output + the GroupNorm(+SiLU) that consumes them

@@ -135,6 +135,14 @@ int d4d_op_attention(const void* q, const void* k, const void* v, int ld_qkv, vo
                      int seq, int heads, int head_dim, float scale, void* stream);
 int d4d_op_groupnorm(const void* x1, int C1, const void* x2, int C2, int n_img, int hw, int groups, float eps,
                      const float* gamma, const float* beta, int silu, void* out, void* stream);
+/* The two resampling convolutions of the UNet, read / written in place (no im2col, no materialised upsampled tensor):
+ *   kind 1: 3x3 stride-2 pad-1 conv (diffusers Downsample2D): x [n,H,W,Cin] -> out [n,H/2,W/2,Cout], Wt [Cout][9][Cin];
+ *   kind 2: one sub-pixel phase (up_a, up_b in {0,1}) of "nearest x2 upsample, then 3x3 pad-1 conv" (Upsample2D): a 2x2 conv on
+ *           the low-resolution x with pre-summed weights Wt [Cout][4][Cin] (tap = ty*2+tx; rows {-1,0} for up_a = 0, {0,+1} for
+ *           up_a = 1, same for columns), written to pixels (2y+up_a, 2x+up_b) of out [n,2H,2W,Cout].  Four calls fill out;
+ *   kind 3: all four phases in one launch, Wt [4 (= up_a*2+up_b)][Cout][4][Cin] (what the UNet plan uses). */
+int d4d_op_conv_resample(const void* x_nhwc, int n_img, int H, int W, int Cin, const void* Wt, int Cout, const float* bias,
+                         int kind, int up_a, int up_b, void* out, void* stream);
 /* conv3x3 (+bias, +residual) whose epilogue accumulates the per-(image, channel) sums of its output, followed by the
  * GroupNorm(+SiLU) that reads those sums instead of running a statistics pass: the pair every ResnetBlock2D of the UNet
  * executes (needs H*W % 32 == 0).  conv_out [n,H,W,Cout] and gn_out [n,H,W,Cout] are both written. */

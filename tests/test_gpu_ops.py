@@ -175,6 +175,23 @@ def test_groupnorm(cuda, n, hw, C1, C2, silu, eps):
     _close(out, ref)
 
 
+@pytest.mark.parametrize("n,H,W,Cin,Cout", [(2, 16, 16, 64, 64), (3, 8, 8, 320, 320), (2, 32, 32, 128, 128), (2, 16, 24, 64, 128),
+                                            (1, 64, 64, 320, 320)])
+def test_resampling_convs(cuda, n, H, W, Cin, Cout):
+    """Downsample2D (3x3 stride 2 through a strided tensor map) and Upsample2D (nearest x2 + 3x3 as four sub-pixel phases)."""
+    from diffuman4d_b200 import ops
+    x = _rand((n, H, W, Cin), 91)
+    w = _rand((Cout, Cin, 3, 3), 92, std=(9 * Cin) ** -0.5)
+    bias = torch.randn(Cout, generator=torch.Generator().manual_seed(93)).cuda()
+    xc = x.float().permute(0, 3, 1, 2)
+    down = ops.conv3x3_stride2(x, ops.conv_weight_to_octi(w), bias)
+    _close(down, F.conv2d(xc, w.float(), bias, stride=2, padding=1).permute(0, 2, 3, 1))
+    ref = F.conv2d(F.interpolate(xc, scale_factor=2.0, mode="nearest"), w.float(), bias, padding=1).permute(0, 2, 3, 1)
+    up = ops.upsample2x_conv3x3(x, w, bias)                                # all four phases in one launch (the UNet plan)
+    _close(up, ref)
+    assert torch.equal(up, ops.upsample2x_conv3x3(x, w, bias, single_launch=False))
+
+
 @pytest.mark.parametrize("n,H,W,Cin,Cout,silu", [(2, 16, 16, 64, 64, True), (3, 8, 8, 320, 640, True), (2, 32, 32, 320, 320, False),
                                                  (2, 16, 24, 128, 256, True), (1, 64, 64, 320, 320, True)])
 def test_conv3x3_fused_groupnorm_stats(cuda, n, H, W, Cin, Cout, silu):
