@@ -38,6 +38,9 @@ void set_error(const std::string& msg);          // thread-local last error (d4d
 // 2-D row-major bf16 matrix [rows, cols] with leading dimension ld (elements); box = {box_cols, box_rows}.
 int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
                  uint32_t box_cols, uint32_t box_rows, int swizzle_bytes);
+// NHWC bf16 tensor [n, h, w, c] as the DESTINATION of 32-row x 32-channel epilogue boxes {32, box_w, box_h, box_n}
+int make_tmap_nhwc_store(CUtensorMap* out, void* base, uint64_t n, uint64_t h, uint64_t w, uint64_t c, uint32_t box_w,
+                         uint32_t box_h, uint32_t box_n);
 // 4-D NHWC bf16 tensor [n, h, w, c]; box = {box_c, box_w, box_h, box_n} ELEMENTS LOADED; `stride` > 1 loads every
 // stride-th pixel along w and h (elementStrides: the box then spans stride * box_w x stride * box_h pixels).
 int make_tmap_nhwc(CUtensorMap* out, const void* base, uint64_t n, uint64_t h, uint64_t w, uint64_t c,
@@ -152,6 +155,24 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* t, uin
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(t)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
       "r"(c3)
       : "memory");
+}
+
+// TMA stores (shared -> global), bulk-group completion.  The writing threads must make their st.shared visible to the
+// async proxy first (fence_proxy_async_smem) and synchronise with the issuing thread.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* t, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(t)), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* t, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(t)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_group_read() {  // <= N groups still READING shared memory
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N> __device__ __forceinline__ void bulk_wait_group() {  // <= N groups not yet complete
+  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
 }
 
 // ---- TMEM ----------------------------------------------------------------------------------

@@ -35,14 +35,22 @@ constexpr int SMEM_BYTES = 227 * 1024;             // everything an SM has: the 
 // Output staging: every epilogue warp owns 32 rows x 64 B.  A thread holds one ROW of the accumulator (TMEM lane), so a
 // direct store makes each warp-level st.global touch 32 different lines (measured: the stores were 50% of the K = 320
 // GEMMs); staged through shared memory the warp stores 8 rows x 64 contiguous bytes per instruction.
+// With TMA stores the staged unit IS the source box of a cp.async.bulk.tensor store (the staging swizzle below is the
+// 64-byte TMA swizzle), double-buffered per warp so that one store can still be reading while the next unit is staged.
+// Only short-K launches (k_blocks <= 20: the store-bound projections) with tiles up to 160 columns get the second staging
+// buffer: it costs a ring stage, and for long main loops the ring depth is what matters (measured: +4 % on the K >= 2560
+// GEMMs / convs with the smaller ring, profiles/README.md).
 constexpr int STG_WARP_BYTES = 32 * 64;
-constexpr int STG_BYTES = 4 * EPI_WARPS_PER_QUARTER * STG_WARP_BYTES;  // 24 KB
-constexpr int RING_BYTES = SMEM_BYTES - 1024 /*align*/ - BAR_BYTES - STG_BYTES;
+constexpr int STG_BYTES1 = 4 * EPI_WARPS_PER_QUARTER * STG_WARP_BYTES;  // 24 KB per set of staging buffers
+__host__ __device__ inline int stg_bufs_for(int block_n, int k_blocks) { return (block_n > 160 || k_blocks > 20) ? 1 : 2; }
+__host__ __device__ inline int ring_bytes_for(int block_n, int k_blocks) {
+  return SMEM_BYTES - 1024 /*align*/ - BAR_BYTES - STG_BYTES1 * stg_bufs_for(block_n, k_blocks);
+}
 // The main loop is bound by the latency of the TMA loads in flight (measured: ~650-700 cycles per k-block whatever block_n
 // is, with 4 x 48 KB stages), so the ring depth follows the tile width: 4 stages at block_n 256 ... 8 at block_n <= 96.
 __host__ __device__ inline int stage_bytes_for(int block_n) { return A_BYTES + block_n * BLOCK_K * 2; }
-__host__ __device__ inline int stages_for(int block_n) {
-  const int s = RING_BYTES / stage_bytes_for(block_n);
+__host__ __device__ inline int stages_for(int block_n, int k_blocks) {
+  const int s = ring_bytes_for(block_n, k_blocks) / stage_bytes_for(block_n);
   return s > MAX_STAGES ? MAX_STAGES : s;
 }
 constexpr int NUM_THREADS = 64 + 128 * EPI_WARPS_PER_QUARTER;  // warp0 TMA, warp1 MMA(+TMEM alloc), then the epilogue warps
@@ -117,17 +125,19 @@ __device__ __forceinline__ float colsum16(float (&v)[16], int lane) {
 template <bool kGeglu>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_a2,
-                 const __grid_constant__ CUtensorMap tmap_b, const GemmKernelArgs a) {
+                 const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_out,
+                 const GemmKernelArgs a) {
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for the 128B swizzle atoms
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
   uint8_t* staging = smem + BAR_BYTES;
-  smem += BAR_BYTES + STG_BYTES;
+  const int STG_BUFS = stg_bufs_for(a.block_n, a.k_blocks);
+  smem += BAR_BYTES + STG_BYTES1 * STG_BUFS;
   uint64_t* full = bars;                   // [MAX_STAGES]
   uint64_t* empty = bars + MAX_STAGES;     // [MAX_STAGES]
   uint64_t* tfull = bars + 2 * MAX_STAGES; // [2]
-  const int STAGES = stages_for(a.block_n);
+  const int STAGES = stages_for(a.block_n, a.k_blocks);
   const int STAGE_BYTES = stage_bytes_for(a.block_n);
   uint64_t* tempty = tfull + 2;        // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
@@ -250,10 +260,12 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const int q = warp & 3;
     const int unit0 = (warp - 2) >> 2;
     const int r = q * 32 + lane;  // row within the 128-row tile
-    uint8_t* stg = staging + (warp - 2) * STG_WARP_BYTES;
-    // staging layout: row-in-warp * 64 B + (16-byte piece ^ swizzle(row)); conflict-free for the row-wise writes and for
-    // the transposed reads (lane -> row = 8 i + lane / 4, piece = lane % 4)
-    const uint32_t stg_w = smem_u32(stg) + lane * 64;
+    uint8_t* stg_base = staging + (warp - 2) * STG_WARP_BYTES * STG_BUFS;
+    uint8_t* stg = stg_base;  // current staging buffer of this warp (alternates per unit)
+    int stg_sel = 0;
+    // staging layout: row-in-warp * 64 B + (16-byte piece ^ swizzle(row)) = CU_TENSOR_MAP_SWIZZLE_64B; conflict-free for the
+    // row-wise writes and for the transposed reads (lane -> row = 8 i + lane / 4, piece = lane % 4)
+    uint32_t stg_w = smem_u32(stg) + lane * 64;
     const int sw_w = (lane >> 1) & 3;
     const int t_piece = lane & 3;
     auto chunk_at = [&](int k) { return 2 * (unit0 + EPI_WARPS_PER_QUARTER * (k >> 1)) + (k & 1); };
@@ -303,6 +315,31 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
       // flush one staged unit: `pieces` = 2 (one 16-column chunk) or 4; ocol = first output column of the unit
       auto flush = [&](int pieces, int ocol) {
+        if (a.tma_store && pieces == 4) {
+          // the staged [32 rows][32 columns] unit is the source box of one TMA store (rows / columns outside the tensor
+          // are clipped by the tensor map); the other staging buffer takes the next unit while this one is being read
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0 && !D4D_DBG(a, 32)) {
+            if (a.mode == 0) {
+              tma_store_2d(&tmap_out, stg, ocol, tc.m0 + q * 32);
+            } else {
+              const int r2 = (q * 32) / a.BW;
+              tma_store_4d(&tmap_out, stg, ocol, tc.x0, tc.y0 + r2 % a.BH, tc.n_img0 + r2 / a.BH);
+            }
+            bulk_commit_group();
+          }
+          if (STG_BUFS == 2) {
+            stg_sel ^= 1;
+            stg = stg_base + stg_sel * STG_WARP_BYTES;
+            stg_w = smem_u32(stg) + lane * 64;
+            if (lane == 0) bulk_wait_group_read<1>();  // the store that last read the buffer we switch to has drained it
+          } else {
+            if (lane == 0) bulk_wait_group_read<0>();  // single buffer: wait until this store has read it
+          }
+          __syncwarp();
+          return;
+        }
         __syncwarp();
         uint4 t[4];
 #pragma unroll
@@ -495,6 +532,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
     }
+    if (lane == 0) bulk_wait_group<0>();  // TMA stores of this warp have been written before the CTA retires
   }
 
   tc_fence_before();
@@ -634,6 +672,27 @@ int gemm_prepare(const GemmDesc& d, GemmLaunch* L) {
     const uint64_t kw = static_cast<uint64_t>(a.n_taps) * d.Cin;
     if (int rc = make_tmap_2d(&L->tmap_b, d.Wt, static_cast<uint64_t>(d.N) * a.n_phases, kw, kw, BLOCK_K, bn, 128)) return rc;
   }
+  // TMA-store epilogue: plain GEMMs and unit-stride convs whose rows are 16-byte aligned (not the fused K/V scatter, not
+  // GEGLU, not the sub-pixel phase convs whose output pixels are strided)
+  a.tma_store = 0;
+  L->tmap_out = L->tmap_a;
+  // ... and only short main loops (k_blocks <= 24), where the epilogue is what bounds the kernel: for long-K tiles the
+  // row-segment stores hide under the main loop and the TMA path measured slightly slower
+  if (!d.geglu && d.kv_world == 0 && a.k_blocks <= 24 && (reinterpret_cast<uintptr_t>(d.out) & 15) == 0 && d.ldo % 8 == 0) {
+    if (!d.conv) {
+      if (d.M >= 32 && d.N >= 32) {  // (boxes never exceed the tensor)
+        if (int rc = make_tmap_2d(&L->tmap_out, d.out, d.M, d.N, d.ldo, 32, 32, 64)) return rc;
+        a.tma_store = 1;
+      }
+    } else if (d.conv_kind <= 1 && d.ldo == d.N && d.N >= 32) {
+      const int bhq = a.BH < 32 / a.BW ? a.BH : 32 / a.BW;
+      const int bnq = 32 / (a.BW * bhq);
+      if (d.n_img >= bnq && a.out_H >= bhq && a.out_W >= a.BW) {
+        if (int rc = make_tmap_nhwc_store(&L->tmap_out, d.out, d.n_img, a.out_H, a.out_W, d.N, a.BW, bhq, bnq)) return rc;
+        a.tma_store = 1;
+      }
+    }
+  }
   int dev = 0, sms = 0;
   D4D_CUDA_OK(cudaGetDevice(&dev));
   D4D_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -646,10 +705,10 @@ int gemm_run(const GemmLaunch& L, cudaStream_t stream) {
   static PerDeviceOnce attr_once[2];
   if (L.args.geglu) {
     if (int rc = ensure_dyn_smem(gemm_umma_kernel<true>, SMEM_BYTES, attr_once[1])) return rc;
-    D4D_CUDA_OK(launch_pdl(gemm_umma_kernel<true>, dim3(L.grid), dim3(NUM_THREADS), SMEM_BYTES, stream, L.tmap_a, L.tmap_a2, L.tmap_b, L.args));
+    D4D_CUDA_OK(launch_pdl(gemm_umma_kernel<true>, dim3(L.grid), dim3(NUM_THREADS), SMEM_BYTES, stream, L.tmap_a, L.tmap_a2, L.tmap_b, L.tmap_out, L.args));
   } else {
     if (int rc = ensure_dyn_smem(gemm_umma_kernel<false>, SMEM_BYTES, attr_once[0])) return rc;
-    D4D_CUDA_OK(launch_pdl(gemm_umma_kernel<false>, dim3(L.grid), dim3(NUM_THREADS), SMEM_BYTES, stream, L.tmap_a, L.tmap_a2, L.tmap_b, L.args));
+    D4D_CUDA_OK(launch_pdl(gemm_umma_kernel<false>, dim3(L.grid), dim3(NUM_THREADS), SMEM_BYTES, stream, L.tmap_a, L.tmap_a2, L.tmap_b, L.tmap_out, L.args));
   }
   D4D_CUDA_OK(cudaGetLastError());
   return 0;

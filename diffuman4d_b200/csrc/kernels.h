@@ -40,6 +40,7 @@ struct GemmKernelArgs {
   bf16* out;
   int ldo;
   int geglu;
+  int tma_store;    // 1: 32-row x 32-column epilogue units leave through TMA stores (tmap_out) instead of st.global
   int act;          // 0 none, 1 SiLU applied to (acc + bias + rowvec) before scale/residual
   float out_scale;  // multiplies (acc + bias + rowvec) after the activation
   // fused GroupNorm statistics of the OUTPUT tensor: per (image, column) sum and sum of squares in 64-bit FIXED POINT
@@ -91,7 +92,7 @@ struct GemmDesc {
 };
 
 struct GemmLaunch {
-  CUtensorMap tmap_a, tmap_a2, tmap_b;
+  CUtensorMap tmap_a, tmap_a2, tmap_b, tmap_out;
   GemmKernelArgs args;
   int grid;
 };
