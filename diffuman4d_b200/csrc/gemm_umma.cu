@@ -519,13 +519,15 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             o0.z = pack_bf16x2(o[4], o[5]);   o0.w = pack_bf16x2(o[6], o[7]);
             o1.x = pack_bf16x2(o[8], o[9]);   o1.y = pack_bf16x2(o[10], o[11]);
             o1.z = pack_bf16x2(o[12], o[13]); o1.w = pack_bf16x2(o[14], o[15]);
-            // direct row-wise stores: this epilogue is bound by the GEGLU math, staging only adds to it (measured)
-            if (!D4D_DBG(a, 32)) {
+            if (a.tma_store) {
+              stage_half(k & 1, o0, o1);  // staged unit -> one TMA store (the one-MUFU GELU left the stores as the bound)
+            } else if (!D4D_DBG(a, 32)) {  // direct row-wise stores
               uint4* op = reinterpret_cast<uint4*>(a.out + static_cast<size_t>(row) * a.ldo + n_tile * half + c * 16);
               op[0] = o0;
               op[1] = o1;
             }
           }
+          if (a.tma_store && ((k & 1) || c + 1 >= chunks)) flush((k & 1) ? 4 : 2, n_tile * half + (c & ~1) * 16);
         }
       }
       tc_fence_before();
@@ -673,15 +675,18 @@ int gemm_prepare(const GemmDesc& d, GemmLaunch* L) {
     if (int rc = make_tmap_2d(&L->tmap_b, d.Wt, static_cast<uint64_t>(d.N) * a.n_phases, kw, kw, BLOCK_K, bn, 128)) return rc;
   }
   // TMA-store epilogue: plain GEMMs and unit-stride convs whose rows are 16-byte aligned (not the fused K/V scatter, not
-  // GEGLU, not the sub-pixel phase convs whose output pixels are strided)
+  // the sub-pixel phase convs whose output pixels are strided)
   a.tma_store = 0;
   L->tmap_out = L->tmap_a;
   // ... and only short main loops (k_blocks <= 24), where the epilogue is what bounds the kernel: for long-K tiles the
   // row-segment stores hide under the main loop and the TMA path measured slightly slower
-  if (!d.geglu && d.kv_world == 0 && a.k_blocks <= 24 && (reinterpret_cast<uintptr_t>(d.out) & 15) == 0 && d.ldo % 8 == 0) {
+  if (d.kv_world == 0 && a.k_blocks <= 24 && (reinterpret_cast<uintptr_t>(d.out) & 15) == 0 && d.ldo % 8 == 0) {
     if (!d.conv) {
-      if (d.M >= 32 && d.N >= 32) {  // (boxes never exceed the tensor)
-        if (int rc = make_tmap_2d(&L->tmap_out, d.out, d.M, d.N, d.ldo, 32, 32, 64)) return rc;
+      const int out_cols = d.geglu ? d.N / 2 : d.N;
+      // GEGLU: every unit must be a full 32 columns (the fallback of an odd last chunk is the row-segment path, which the
+      // GEGLU branch does not carry)
+      if (d.M >= 32 && out_cols >= 32 && (!d.geglu || (bn / 2) % 32 == 0)) {  // (boxes never exceed the tensor)
+        if (int rc = make_tmap_2d(&L->tmap_out, d.out, d.M, out_cols, d.ldo, 32, 32, 64)) return rc;
         a.tma_store = 1;
       }
     } else if (d.conv_kind <= 1 && d.ldo == d.N && d.N >= 32) {
