@@ -410,7 +410,17 @@ int groupnorm_apply_run(const bf16* x1, int C1, const long long* stats1, const b
   if (a.rows_per_iter < 1) a.rows_per_iter = 1;
   if (a.rows_per_iter > 8) a.rows_per_iter = 8;
   a.hw = hw;
-  a.splits = groupnorm_splits(hw);
+  // one wave of CTAs (2 per SM): every CTA pays the group-statistics prologue once, so fewer and longer CTAs than the
+  // stand-alone path (which sizes its slabs for the partials it has to merge)
+  {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int sp = (2 * sms) / n_img;
+    const int cap = groupnorm_splits(hw);
+    a.splits = sp < 1 ? 1 : (sp > cap ? cap : sp);
+  }
+
   a.pps = (hw + a.splits - 1) / a.splits;
   a.groups = groups;
   a.cpg = C / groups;
