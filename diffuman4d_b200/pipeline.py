@@ -44,6 +44,17 @@ def build_windows(target_indices: torch.Tensor, input_indices: torch.Tensor, dom
     return target_windows, input_windows
 
 
+def resize_conditions(plucker_embeds: torch.Tensor, cond_masks: torch.Tensor, h: int, w: int, dtype: torch.dtype):
+    """Latent-resolution conditioning maps on whatever device the inputs live on (PIPE:90-100, 215-226): Pluecker channels
+    bilinearly, masks with nearest; both resizes run in the SOURCE dtype and are cast afterwards, like the reference."""
+    plk, msk = plucker_embeds, cond_masks
+    if plk.shape[-2:] != (h, w):
+        plk = torch.nn.functional.interpolate(plk, size=(h, w), mode="bilinear")
+    if msk.shape[-2:] != (h, w):
+        msk = torch.nn.functional.interpolate(msk, size=(h, w), mode="nearest")
+    return plk.to(dtype), msk.to(dtype)
+
+
 class B200Diffuman4DPipeline:
     def __init__(self, unet: B200MultiviewUNet, scheduler_config: Optional[SchedulerConfig] = None, vae=None,
                  emulate_bf16_scheduler: bool = False):
@@ -176,14 +187,7 @@ class B200Diffuman4DPipeline:
             pixel_values_latents = self.vae.encode_latents(pixel_values.to(dev, torch.bfloat16))
         pixel_values_latents = pixel_values_latents.to(dev, torch.bfloat16)
         n, _, h, w = pixel_values_latents.shape
-        plk = plucker_embeds.to(dev)
-        if plk.shape[-2:] != (h, w):
-            plk = torch.nn.functional.interpolate(plk, size=(h, w), mode="bilinear")
-        plk = plk.to(torch.bfloat16)
-        msk = cond_masks.to(dev)
-        if msk.shape[-2:] != (h, w):
-            msk = torch.nn.functional.interpolate(msk, size=(h, w), mode="nearest")
-        msk = msk.to(torch.bfloat16)
+        plk, msk = resize_conditions(plucker_embeds.to(dev), cond_masks.to(dev), h, w, torch.bfloat16)
         if skeletons_latents is not None:                      # same precedence as PIPE:228-241
             skl = skeletons_latents.to(dev, torch.bfloat16)
         elif self.unet.config.enable_pose_encoder:
