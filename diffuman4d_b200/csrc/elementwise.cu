@@ -110,9 +110,11 @@ __global__ void nhwc_to_nchw_kernel(const bf16* __restrict__ x, int ld, int n, i
 
 // ---------------------------------------------------------------------------------------------
 // direct small-channel convolution (pose encoder, pose_encoder.py:14-31): pad 1, k in {3,4}, stride {1,2}
-// one thread per output pixel, COUT accumulators in registers, weights [k*k][Cin][COUT] fp32 in smem
+// one thread per PIX horizontally adjacent output pixels, PIX x COUT accumulators in registers, weights [k*k][Cin][COUT] fp32
+// in smem (every weight read from shared memory - a warp-wide broadcast - feeds PIX FMAs: with one pixel per thread the
+// kernel was bound by those broadcasts, not by the FMAs)
 // ---------------------------------------------------------------------------------------------
-template <int COUT>
+template <int COUT, int PIX>
 __global__ void direct_conv_kernel(const bf16* __restrict__ x, int in_nchw, int n, int Cin, int H, int W,
                                    const bf16* __restrict__ w, const float* __restrict__ bias, int ksize, int stride,
                                    int silu, float out_scale, bf16* __restrict__ out) {
@@ -121,61 +123,93 @@ __global__ void direct_conv_kernel(const bf16* __restrict__ x, int in_nchw, int 
   for (int i = threadIdx.x; i < kk * Cin * COUT; i += blockDim.x) sw[i] = __bfloat162float(w[i]);
   __syncthreads();
   const int Ho = (H + 2 - ksize) / stride + 1, Wo = (W + 2 - ksize) / stride + 1;
-  const long long total = static_cast<long long>(n) * Ho * Wo;
-  const long long pix = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (pix >= total) return;
-  const int xo = static_cast<int>(pix % Wo);
-  const int yo = static_cast<int>((pix / Wo) % Ho);
-  const int img = static_cast<int>(pix / (static_cast<long long>(Wo) * Ho));
-  float acc[COUT];
+  const int Wg = (Wo + PIX - 1) / PIX;  // pixel groups per row
+  const long long total = static_cast<long long>(n) * Ho * Wg;
+  const long long grp = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (grp >= total) return;
+  const int xo0 = static_cast<int>(grp % Wg) * PIX;
+  const int yo = static_cast<int>((grp / Wg) % Ho);
+  const int img = static_cast<int>(grp / (static_cast<long long>(Wg) * Ho));
+  float acc[PIX][COUT];
 #pragma unroll
-  for (int i = 0; i < COUT; ++i) acc[i] = bias ? bias[i] : 0.f;
+  for (int p = 0; p < PIX; ++p)
+#pragma unroll
+    for (int i = 0; i < COUT; ++i) acc[p][i] = bias ? bias[i] : 0.f;
   for (int ky = 0; ky < ksize; ++ky) {
     const int yy = yo * stride + ky - 1;
     if (yy < 0 || yy >= H) continue;
     for (int kx = 0; kx < ksize; ++kx) {
-      const int xx = xo * stride + kx - 1;
-      if (xx < 0 || xx >= W) continue;
       const float* wt = sw + static_cast<size_t>(ky * ksize + kx) * Cin * COUT;
+      int xx[PIX];
+      bool ok[PIX];
+#pragma unroll
+      for (int p = 0; p < PIX; ++p) {
+        xx[p] = (xo0 + p) * stride + kx - 1;
+        ok[p] = xx[p] >= 0 && xx[p] < W;  // (pixels past the row end read a clamped address and are not stored)
+        if (!ok[p]) xx[p] = 0;
+      }
       if (in_nchw) {
         for (int c = 0; c < Cin; ++c) {
-          const float v = __bfloat162float(x[((static_cast<size_t>(img) * Cin + c) * H + yy) * W + xx]);
+          float v[PIX];
 #pragma unroll
-          for (int i = 0; i < COUT; ++i) acc[i] = fmaf(v, wt[c * COUT + i], acc[i]);
+          for (int p = 0; p < PIX; ++p)
+            v[p] = ok[p] ? __bfloat162float(x[((static_cast<size_t>(img) * Cin + c) * H + yy) * W + xx[p]]) : 0.f;
+#pragma unroll
+          for (int i = 0; i < COUT; ++i) {
+            const float wv = wt[c * COUT + i];
+#pragma unroll
+            for (int p = 0; p < PIX; ++p) acc[p][i] = fmaf(v[p], wv, acc[p][i]);
+          }
         }
-      } else {
-        const bf16* px = x + ((static_cast<size_t>(img) * H + yy) * W + xx) * Cin;
-        if (Cin % 8 == 0) {
-          for (int c8 = 0; c8 < Cin; c8 += 8) {
-            const uint4 u = __ldg(reinterpret_cast<const uint4*>(px + c8));
-            float f[8];
-            float2 p;
-            p = unpack_bf16x2(u.x); f[0] = p.x; f[1] = p.y;
-            p = unpack_bf16x2(u.y); f[2] = p.x; f[3] = p.y;
-            p = unpack_bf16x2(u.z); f[4] = p.x; f[5] = p.y;
-            p = unpack_bf16x2(u.w); f[6] = p.x; f[7] = p.y;
+      } else if (Cin % 8 == 0) {
+        for (int c8 = 0; c8 < Cin; c8 += 8) {
+          float f[PIX][8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+          for (int p = 0; p < PIX; ++p) {
+            uint4 u = make_uint4(0u, 0u, 0u, 0u);
+            if (ok[p]) u = __ldg(reinterpret_cast<const uint4*>(x + ((static_cast<size_t>(img) * H + yy) * W + xx[p]) * Cin + c8));
+            float2 q;
+            q = unpack_bf16x2(u.x); f[p][0] = q.x; f[p][1] = q.y;
+            q = unpack_bf16x2(u.y); f[p][2] = q.x; f[p][3] = q.y;
+            q = unpack_bf16x2(u.z); f[p][4] = q.x; f[p][5] = q.y;
+            q = unpack_bf16x2(u.w); f[p][6] = q.x; f[p][7] = q.y;
+          }
 #pragma unroll
-              for (int i = 0; i < COUT; ++i) acc[i] = fmaf(f[j], wt[(c8 + j) * COUT + i], acc[i]);
+          for (int j = 0; j < 8; ++j) {
+#pragma unroll
+            for (int i = 0; i < COUT; ++i) {
+              const float wv = wt[(c8 + j) * COUT + i];
+#pragma unroll
+              for (int p = 0; p < PIX; ++p) acc[p][i] = fmaf(f[p][j], wv, acc[p][i]);
             }
           }
-        } else {
-          for (int c = 0; c < Cin; ++c) {
-            const float v = __bfloat162float(px[c]);
+        }
+      } else {
+        for (int c = 0; c < Cin; ++c) {
+          float v[PIX];
 #pragma unroll
-            for (int i = 0; i < COUT; ++i) acc[i] = fmaf(v, wt[c * COUT + i], acc[i]);
+          for (int p = 0; p < PIX; ++p)
+            v[p] = ok[p] ? __bfloat162float(x[((static_cast<size_t>(img) * H + yy) * W + xx[p]) * Cin + c]) : 0.f;
+#pragma unroll
+          for (int i = 0; i < COUT; ++i) {
+            const float wv = wt[c * COUT + i];
+#pragma unroll
+            for (int p = 0; p < PIX; ++p) acc[p][i] = fmaf(v[p], wv, acc[p][i]);
           }
         }
       }
     }
   }
-  bf16* o = out + pix * COUT;
 #pragma unroll
-  for (int i = 0; i < COUT; ++i) {
-    float y = acc[i];
-    if (silu) y = silu_f(y);
-    o[i] = __float2bfloat16_rn(y * out_scale);
+  for (int p = 0; p < PIX; ++p) {
+    if (xo0 + p >= Wo) break;
+    bf16* o = out + ((static_cast<size_t>(img) * Ho + yo) * Wo + xo0 + p) * COUT;
+#pragma unroll
+    for (int i = 0; i < COUT; ++i) {
+      float y = acc[p][i];
+      if (silu) y = silu_f(y);
+      o[i] = __float2bfloat16_rn(y * out_scale);
+    }
   }
 }
 
@@ -408,17 +442,19 @@ int direct_conv_run(const bf16* x, int in_nchw, int n, int Cin, int H, int W, co
   const size_t smem = sizeof(float) * ksize * ksize * Cin * Cout;
   D4D_REQUIRE(smem <= 48 * 1024, "direct conv weights exceed 48 KB of shared memory");
   const int threads = 128;
-  const int blocks = blocks_for(total, threads);
-#define D4D_DC(CO)                                                                                                 \
-  case CO:                                                                                                         \
-    direct_conv_kernel<CO><<<blocks, threads, smem, stream>>>(x, in_nchw, n, Cin, H, W, w, bias, ksize, stride, silu, \
-                                                              out_scale, out_nhwc);                                \
-    break;
+  // pixels per thread: 4 for few output channels, 2 for 32 (64 accumulators), 1 for 64
+#define D4D_DC(CO, PX)                                                                                                 \
+  case CO: {                                                                                                           \
+    const long long groups = static_cast<long long>(n) * Ho * ((Wo + PX - 1) / PX);                                     \
+    direct_conv_kernel<CO, PX><<<blocks_for(groups, threads), threads, smem, stream>>>(x, in_nchw, n, Cin, H, W, w, bias, \
+                                                                                       ksize, stride, silu, out_scale,  \
+                                                                                       out_nhwc);                       \
+  } break;
   switch (Cout) {
-    D4D_DC(3)
-    D4D_DC(16)
-    D4D_DC(32)
-    D4D_DC(64)
+    D4D_DC(3, 4)
+    D4D_DC(16, 4)
+    D4D_DC(32, 2)
+    D4D_DC(64, 1)
     default:
       set_error("direct conv: unsupported Cout " + std::to_string(Cout));
       return 1;
