@@ -109,106 +109,154 @@ __global__ void nhwc_to_nchw_kernel(const bf16* __restrict__ x, int ld, int n, i
 }
 
 // ---------------------------------------------------------------------------------------------
-// direct small-channel convolution (pose encoder, pose_encoder.py:14-31): pad 1, k in {3,4}, stride {1,2}
-// one thread per PIX horizontally adjacent output pixels, PIX x COUT accumulators in registers, weights [k*k][Cin][COUT] fp32
-// in smem (every weight read from shared memory - a warp-wide broadcast - feeds PIX FMAs: with one pixel per thread the
-// kernel was bound by those broadcasts, not by the FMAs)
+// pose encoder, first layer (pose_encoder.py:14-31, conv_layers.0): 3 -> 3 channels, 3x3, stride 1, pad 1, SiLU, on the
+// full-resolution NCHW skeleton images.  One thread per kPix0 horizontally adjacent output pixels (every weight read from
+// shared memory - a warp-wide broadcast - feeds kPix0 FMAs); the output is NHWC with the 3 channels padded to 4 (8-byte
+// pixels, channel 3 = 0), the layout the tensor-core layers below read.
 // ---------------------------------------------------------------------------------------------
-template <int COUT, int PIX>
-__global__ void direct_conv_kernel(const bf16* __restrict__ x, int in_nchw, int n, int Cin, int H, int W,
-                                   const bf16* __restrict__ w, const float* __restrict__ bias, int ksize, int stride,
-                                   int silu, float out_scale, bf16* __restrict__ out) {
-  extern __shared__ float sw[];  // [k*k*Cin][COUT]
-  const int kk = ksize * ksize;
-  for (int i = threadIdx.x; i < kk * Cin * COUT; i += blockDim.x) sw[i] = __bfloat162float(w[i]);
+constexpr int kPix0 = 4;
+__global__ void pose_conv0_kernel(const bf16* __restrict__ x, int n, int H, int W, const bf16* __restrict__ w /*[9][3][3]*/,
+                                  const float* __restrict__ bias, bf16* __restrict__ out /*[n,H,W,4]*/) {
+  __shared__ float sw[81];
+  if (threadIdx.x < 81) sw[threadIdx.x] = __bfloat162float(w[threadIdx.x]);
   __syncthreads();
-  const int Ho = (H + 2 - ksize) / stride + 1, Wo = (W + 2 - ksize) / stride + 1;
-  const int Wg = (Wo + PIX - 1) / PIX;  // pixel groups per row
-  const long long total = static_cast<long long>(n) * Ho * Wg;
+  const int Wg = (W + kPix0 - 1) / kPix0;
+  const long long total = static_cast<long long>(n) * H * Wg;
   const long long grp = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (grp >= total) return;
-  const int xo0 = static_cast<int>(grp % Wg) * PIX;
-  const int yo = static_cast<int>((grp / Wg) % Ho);
-  const int img = static_cast<int>(grp / (static_cast<long long>(Wg) * Ho));
-  float acc[PIX][COUT];
+  const int xo0 = static_cast<int>(grp % Wg) * kPix0;
+  const int yo = static_cast<int>((grp / Wg) % H);
+  const int img = static_cast<int>(grp / (static_cast<long long>(Wg) * H));
+  float acc[kPix0][3];
 #pragma unroll
-  for (int p = 0; p < PIX; ++p)
+  for (int p = 0; p < kPix0; ++p)
 #pragma unroll
-    for (int i = 0; i < COUT; ++i) acc[p][i] = bias ? bias[i] : 0.f;
-  for (int ky = 0; ky < ksize; ++ky) {
-    const int yy = yo * stride + ky - 1;
+    for (int i = 0; i < 3; ++i) acc[p][i] = bias[i];
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky) {
+    const int yy = yo + ky - 1;
     if (yy < 0 || yy >= H) continue;
-    for (int kx = 0; kx < ksize; ++kx) {
-      const float* wt = sw + static_cast<size_t>(ky * ksize + kx) * Cin * COUT;
-      int xx[PIX];
-      bool ok[PIX];
 #pragma unroll
-      for (int p = 0; p < PIX; ++p) {
-        xx[p] = (xo0 + p) * stride + kx - 1;
-        ok[p] = xx[p] >= 0 && xx[p] < W;  // (pixels past the row end read a clamped address and are not stored)
-        if (!ok[p]) xx[p] = 0;
+    for (int c = 0; c < 3; ++c) {
+      const bf16* row = x + ((static_cast<size_t>(img) * 3 + c) * H + yy) * W;
+      float v[kPix0 + 2];  // input columns xo0-1 .. xo0+kPix0
+#pragma unroll
+      for (int j = 0; j < kPix0 + 2; ++j) {
+        const int xx = xo0 + j - 1;
+        v[j] = (xx >= 0 && xx < W) ? __bfloat162float(row[xx]) : 0.f;
       }
-      if (in_nchw) {
-        for (int c = 0; c < Cin; ++c) {
-          float v[PIX];
 #pragma unroll
-          for (int p = 0; p < PIX; ++p)
-            v[p] = ok[p] ? __bfloat162float(x[((static_cast<size_t>(img) * Cin + c) * H + yy) * W + xx[p]]) : 0.f;
+      for (int kx = 0; kx < 3; ++kx)
 #pragma unroll
-          for (int i = 0; i < COUT; ++i) {
-            const float wv = wt[c * COUT + i];
+        for (int i = 0; i < 3; ++i) {
+          const float wv = sw[((ky * 3 + kx) * 3 + c) * 3 + i];
 #pragma unroll
-            for (int p = 0; p < PIX; ++p) acc[p][i] = fmaf(v[p], wv, acc[p][i]);
-          }
+          for (int p = 0; p < kPix0; ++p) acc[p][i] = fmaf(v[p + kx], wv, acc[p][i]);
         }
-      } else if (Cin % 8 == 0) {
-        for (int c8 = 0; c8 < Cin; c8 += 8) {
-          float f[PIX][8];
-#pragma unroll
-          for (int p = 0; p < PIX; ++p) {
-            uint4 u = make_uint4(0u, 0u, 0u, 0u);
-            if (ok[p]) u = __ldg(reinterpret_cast<const uint4*>(x + ((static_cast<size_t>(img) * H + yy) * W + xx[p]) * Cin + c8));
-            float2 q;
-            q = unpack_bf16x2(u.x); f[p][0] = q.x; f[p][1] = q.y;
-            q = unpack_bf16x2(u.y); f[p][2] = q.x; f[p][3] = q.y;
-            q = unpack_bf16x2(u.z); f[p][4] = q.x; f[p][5] = q.y;
-            q = unpack_bf16x2(u.w); f[p][6] = q.x; f[p][7] = q.y;
-          }
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-#pragma unroll
-            for (int i = 0; i < COUT; ++i) {
-              const float wv = wt[(c8 + j) * COUT + i];
-#pragma unroll
-              for (int p = 0; p < PIX; ++p) acc[p][i] = fmaf(f[p][j], wv, acc[p][i]);
-            }
-          }
-        }
-      } else {
-        for (int c = 0; c < Cin; ++c) {
-          float v[PIX];
-#pragma unroll
-          for (int p = 0; p < PIX; ++p)
-            v[p] = ok[p] ? __bfloat162float(x[((static_cast<size_t>(img) * H + yy) * W + xx[p]) * Cin + c]) : 0.f;
-#pragma unroll
-          for (int i = 0; i < COUT; ++i) {
-            const float wv = wt[c * COUT + i];
-#pragma unroll
-            for (int p = 0; p < PIX; ++p) acc[p][i] = fmaf(v[p], wv, acc[p][i]);
-          }
-        }
-      }
     }
   }
 #pragma unroll
-  for (int p = 0; p < PIX; ++p) {
-    if (xo0 + p >= Wo) break;
-    bf16* o = out + ((static_cast<size_t>(img) * Ho + yo) * Wo + xo0 + p) * COUT;
+  for (int p = 0; p < kPix0; ++p) {
+    if (xo0 + p >= W) break;
+    uint2 o;
+    o.x = pack_bf16x2(silu_f(acc[p][0]), silu_f(acc[p][1]));
+    o.y = pack_bf16x2(silu_f(acc[p][2]), 0.f);
+    *reinterpret_cast<uint2*>(out + ((static_cast<size_t>(img) * H + yo) * W + xo0 + p) * 4) = o;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// pose encoder, layers 1-4 (conv_layers.2/4/6/8: 3->16 k4 s2, 16->16 k3, 16->32 k4 s2, 32->32 k3; pad 1, SiLU): implicit
+// GEMM on the warp-level tensor-core path (mma.sync m16n8k16, bf16 x bf16 -> fp32).  These layers are 1-3 GMAC each on
+// 16/32 output channels - far too narrow for a tcgen05 tile (the UNet's convs use csrc/gemm_umma.cu) but, one thread per
+// pixel on the FMA pipe, they cost more than a whole 3x3 conv of the UNet.  Here a warp owns 32 output pixels (2 M tiles)
+// x all COUT channels; K = taps x CIN runs in chunks of 16.  The A fragment of m16n8k16 is, per lane, two adjacent
+// channels of one pixel at one tap = one 4-byte load straight from the NHWC activation (L1 keeps the 9-16x tap reuse);
+// the B fragments come from the [COUT][K+8] weights staged once per CTA in shared memory (the +8 skews the rows over the banks).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mma_bf16_m16n8k16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <int COUT, int CIN, int KS, int STRIDE>
+__global__ void __launch_bounds__(256, 2) pose_conv_mma_kernel(const bf16* __restrict__ x, int n, int H, int W,
+                                                               const bf16* __restrict__ w /*[COUT][KS*KS*CIN + 8]*/,
+                                                               const float* __restrict__ bias, bf16* __restrict__ out) {
+  constexpr int K = KS * KS * CIN, KP = K + 8, NT = COUT / 8;
+  static_assert(K % 16 == 0 && CIN % 4 == 0 && COUT % 8 == 0 && (COUT * KP * 2) % 16 == 0, "pose conv tile shape");
+  extern __shared__ __align__(16) unsigned char pose_smem[];
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(w);
+    uint4* dst = reinterpret_cast<uint4*>(pose_smem);
+    for (int i = threadIdx.x; i < COUT * KP * 2 / 16; i += blockDim.x) dst[i] = __ldg(src + i);
+  }
+  __syncthreads();
+  const uint32_t* sw = reinterpret_cast<const uint32_t*>(pose_smem);  // bf16 pairs, row stride KP / 2 words
+  const int Ho = (H + 2 - KS) / STRIDE + 1, Wo = (W + 2 - KS) / STRIDE + 1;
+  const int total = n * Ho * Wo;
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int warps = gridDim.x * (blockDim.x >> 5);
+  float bs[NT][2];
 #pragma unroll
-    for (int i = 0; i < COUT; ++i) {
-      float y = acc[p][i];
-      if (silu) y = silu_f(y);
-      o[i] = __float2bfloat16_rn(y * out_scale);
+  for (int nt = 0; nt < NT; ++nt) {
+    bs[nt][0] = bias[nt * 8 + 2 * t];
+    bs[nt][1] = bias[nt * 8 + 2 * t + 1];
+  }
+  for (int tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); tile * 32 < total; tile += warps) {
+    // this lane's four pixel rows: q = 2 * m_tile + half, fragment row g + 8 * half
+    int y0[4], x0[4], ib[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int p = tile * 32 + (q >> 1) * 16 + (q & 1) * 8 + g;
+      const int pc = p < total ? p : 0;
+      const int xo = pc % Wo, yo = (pc / Wo) % Ho, img = pc / (Wo * Ho);
+      y0[q] = p < total ? yo * STRIDE - 1 : -(1 << 20);  // a row past the end fails every bounds check below: zeros
+      x0[q] = xo * STRIDE - 1;
+      ib[q] = img * H * W * CIN;
+    }
+    float acc[2][NT][4];
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[m][nt][i] = 0.f;
+#pragma unroll
+    for (int ch = 0; ch < K / 16; ++ch) {
+      uint32_t a[2][4];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int k = ch * 16 + h * 8 + 2 * t;  // this lane's channel pair: columns k, k+1 of the im2col row
+        const int tap = k / CIN, c = k % CIN, ky = tap / KS, kx = tap % KS;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int yy = y0[q] + ky, xx = x0[q] + kx;
+          uint32_t v = 0u;
+          if (static_cast<unsigned>(yy) < static_cast<unsigned>(H) && static_cast<unsigned>(xx) < static_cast<unsigned>(W))
+            v = __ldg(reinterpret_cast<const uint32_t*>(x + ib[q] + (yy * W + xx) * CIN + c));
+          a[q >> 1][(q & 1) + 2 * h] = v;
+        }
+      }
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        const uint32_t b0 = sw[((nt * 8 + g) * KP + ch * 16 + 2 * t) >> 1];
+        const uint32_t b1 = sw[((nt * 8 + g) * KP + ch * 16 + 8 + 2 * t) >> 1];
+        mma_bf16_m16n8k16(acc[0][nt], a[0], b0, b1);
+        mma_bf16_m16n8k16(acc[1][nt], a[1], b0, b1);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int p = tile * 32 + (q >> 1) * 16 + (q & 1) * 8 + g;
+      if (p >= total) continue;
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        const float v0 = silu_f(acc[q >> 1][nt][2 * (q & 1)] + bs[nt][0]);
+        const float v1 = silu_f(acc[q >> 1][nt][2 * (q & 1) + 1] + bs[nt][1]);
+        *reinterpret_cast<uint32_t*>(out + static_cast<size_t>(p) * COUT + nt * 8 + 2 * t) = pack_bf16x2(v0, v1);
+      }
     }
   }
 }
@@ -433,35 +481,41 @@ int nhwc_to_nchw_run(const bf16* x, int ld, int n, int C, int hw, bf16* out, cud
   return 0;
 }
 
-int direct_conv_run(const bf16* x, int in_nchw, int n, int Cin, int H, int W, const bf16* w, const float* bias, int Cout,
-                    int ksize, int stride, int silu, float out_scale, bf16* out_nhwc, cudaStream_t stream) {
-  D4D_REQUIRE(ksize == 3 || ksize == 4, "direct conv kernel size");
-  D4D_REQUIRE(stride == 1 || stride == 2, "direct conv stride");
-  const int Ho = (H + 2 - ksize) / stride + 1, Wo = (W + 2 - ksize) / stride + 1;
-  const long long total = static_cast<long long>(n) * Ho * Wo;
-  const size_t smem = sizeof(float) * ksize * ksize * Cin * Cout;
-  D4D_REQUIRE(smem <= 48 * 1024, "direct conv weights exceed 48 KB of shared memory");
-  const int threads = 128;
-  // pixels per thread: 4 for few output channels, 2 for 32 (64 accumulators), 1 for 64
-#define D4D_DC(CO, PX)                                                                                                 \
-  case CO: {                                                                                                           \
-    const long long groups = static_cast<long long>(n) * Ho * ((Wo + PX - 1) / PX);                                     \
-    direct_conv_kernel<CO, PX><<<blocks_for(groups, threads), threads, smem, stream>>>(x, in_nchw, n, Cin, H, W, w, bias, \
-                                                                                       ksize, stride, silu, out_scale,  \
-                                                                                       out_nhwc);                       \
-  } break;
-  switch (Cout) {
-    D4D_DC(3, 4)
-    D4D_DC(16, 4)
-    D4D_DC(32, 2)
-    D4D_DC(64, 1)
-    default:
-      set_error("direct conv: unsupported Cout " + std::to_string(Cout));
-      return 1;
-  }
-#undef D4D_DC
+int pose_conv0_run(const bf16* x_nchw, int n, int H, int W, const bf16* w, const float* bias, bf16* out_nhwc4,
+                   cudaStream_t stream) {
+  const long long groups = static_cast<long long>(n) * H * ((W + kPix0 - 1) / kPix0);
+  pose_conv0_kernel<<<blocks_for(groups, 128), 128, 0, stream>>>(x_nchw, n, H, W, w, bias, out_nhwc4);
   D4D_CUDA_OK(cudaGetLastError());
   return 0;
+}
+
+int pose_conv_run(const bf16* x, int n, int Cin, int H, int W, const bf16* w, const float* bias, int Cout, int ksize,
+                  int stride, bf16* out_nhwc, cudaStream_t stream) {
+  const int Ho = (H + 2 - ksize) / stride + 1, Wo = (W + 2 - ksize) / stride + 1;
+  const long long total = static_cast<long long>(n) * Ho * Wo;
+  D4D_REQUIRE(static_cast<long long>(n) * H * W * Cin < (1ll << 31) && total * Cout < (1ll << 31), "pose conv: 32-bit offsets");
+  D4D_REQUIRE(reinterpret_cast<uintptr_t>(w) % 16 == 0, "pose conv weights must be 16-byte aligned");
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int threads = 256;
+  const long long tiles = (total + 31) / 32;
+  const int blocks = static_cast<int>(std::min<long long>((tiles + threads / 32 - 1) / (threads / 32), 2ll * sms));
+#define D4D_PC(CO, CI, KS, ST)                                                                                          \
+  if (Cout == CO && Cin == CI && ksize == KS && stride == ST) {                                                          \
+    const size_t smem = static_cast<size_t>(CO) * (KS * KS * CI + 8) * 2;                                                 \
+    pose_conv_mma_kernel<CO, CI, KS, ST><<<blocks, threads, smem, stream>>>(x, n, H, W, w, bias, out_nhwc);               \
+    D4D_CUDA_OK(cudaGetLastError());                                                                                     \
+    return 0;                                                                                                            \
+  }
+  D4D_PC(16, 4, 4, 2)
+  D4D_PC(16, 16, 3, 1)
+  D4D_PC(32, 16, 4, 2)
+  D4D_PC(32, 32, 3, 1)
+#undef D4D_PC
+  set_error("pose conv: unsupported layer " + std::to_string(Cin) + "->" + std::to_string(Cout) + " k" + std::to_string(ksize) +
+            " s" + std::to_string(stride));
+  return 1;
 }
 
 int kv_signal_run(const KvFlagArgs& a, cudaStream_t stream) {

@@ -165,10 +165,12 @@ int silu_run(const bf16* x, long long n, bf16* out, cudaStream_t stream);
 int im2col_nchw_run(const bf16* x, int n, int Cin, int H, int W, int cin_pad, int KP, bf16* out, cudaStream_t stream);
 // [n*hw, ld] (first C columns) -> NCHW [n, C, hw]
 int nhwc_to_nchw_run(const bf16* x, int ld, int n, int C, int hw, bf16* out, cudaStream_t stream);
-// direct small-channel conv (pose encoder): NHWC (or NCHW input when in_nchw), pad 1, optional SiLU
-int direct_conv_run(const bf16* x, int in_nchw, int n, int Cin, int H, int W, const bf16* w /*[k*k][Cin][Cout]*/,
-                    const float* bias, int Cout, int ksize, int stride, int silu, float out_scale, bf16* out_nhwc,
-                    cudaStream_t stream);
+// pose encoder layer 0: NCHW [n,3,H,W] -> NHWC [n,H,W,4] (channel 3 = 0), 3x3 pad 1 + SiLU; w [9][3][3] (tap, cin, cout)
+int pose_conv0_run(const bf16* x_nchw, int n, int H, int W, const bf16* w, const float* bias, bf16* out_nhwc4,
+                   cudaStream_t stream);
+// pose encoder layers 1-4 on mma.sync: NHWC in / out, pad 1 + SiLU; w [Cout][k*k*Cin + 8] (K index = tap*Cin + c, zero pad)
+int pose_conv_run(const bf16* x, int n, int Cin, int H, int W, const bf16* w, const float* bias, int Cout, int ksize,
+                  int stride, bf16* out_nhwc, cudaStream_t stream);
 // nearest x2 upsample NHWC
 int upsample2x_run(const bf16* x, int n, int H, int W, int C, bf16* out, cudaStream_t stream);
 // generic NHWC im2col, pad 1: [n,H,W,C] -> [n*Ho*Wo, k*k*C]

@@ -405,12 +405,20 @@ int Model::finalize() {
       l.in = cin;
       l.out = cout;
       l.b = up_f32(T(p + ".bias"));
-      if (i < 5) {  // direct layout [k*k][Cin][Cout]
+      if (i == 0) {  // FMA kernel: [k*k][Cin][Cout]
         std::vector<float> o(w.size());
         for (int co = 0; co < cout; ++co)
           for (int ci = 0; ci < cin; ++ci)
             for (int t = 0; t < k * k; ++t) o[(static_cast<size_t>(t) * cin + ci) * cout + co] = w[(static_cast<size_t>(co) * cin + ci) * k * k + t];
         l.w = up_bf16(o);
+      } else if (i < 5) {  // mma.sync kernel: [Cout][k*k*cin_pad + 8], K index = tap*cin_pad + ci (layer 1 reads 4-channel pixels)
+        const int cp = cin < 4 ? 4 : cin, KP = k * k * cp + 8;
+        std::vector<float> o(static_cast<size_t>(cout) * KP, 0.f);
+        for (int co = 0; co < cout; ++co)
+          for (int ci = 0; ci < cin; ++ci)
+            for (int t = 0; t < k * k; ++t) o[static_cast<size_t>(co) * KP + t * cp + ci] = w[(static_cast<size_t>(co) * cin + ci) * k * k + t];
+        l.w = up_bf16(o);
+        l.in = cp;
       } else {
         l.w = up_bf16(conv_gemm_layout(w, cout, cin, k));
       }
@@ -891,19 +899,19 @@ class PlanBuilder {
       const int PB = p_.pose_shared_neg ? F + 1 : B;
       const int PM0 = PB * h * w;
       const PoseW& pw = m.pose_;
-      bf16* a0 = alloc(static_cast<size_t>(PB) * Hs * Ws * 3);
-      op([=](cudaStream_t s) { return direct_conv_run(pl->skeletons, 1, PB, 3, Hs, Ws, pw.conv[0].w, pw.conv[0].b, 3, 3, 1, 1, 1.f, a0, s); });
+      bf16* a0 = alloc(static_cast<size_t>(PB) * Hs * Ws * 4);  // 3 channels padded to 4
+      op([=](cudaStream_t s) { return pose_conv0_run(pl->skeletons, PB, Hs, Ws, pw.conv[0].w, pw.conv[0].b, a0, s); });
       bf16* a1 = alloc(static_cast<size_t>(PB) * (Hs / 2) * (Ws / 2) * 16);
-      op([=](cudaStream_t s) { return direct_conv_run(a0, 0, PB, 3, Hs, Ws, pw.conv[1].w, pw.conv[1].b, 16, 4, 2, 1, 1.f, a1, s); });
+      op([=](cudaStream_t s) { return pose_conv_run(a0, PB, 4, Hs, Ws, pw.conv[1].w, pw.conv[1].b, 16, 4, 2, a1, s); });
       release(a0);
       bf16* a2 = alloc(static_cast<size_t>(PB) * (Hs / 2) * (Ws / 2) * 16);
-      op([=](cudaStream_t s) { return direct_conv_run(a1, 0, PB, 16, Hs / 2, Ws / 2, pw.conv[2].w, pw.conv[2].b, 16, 3, 1, 1, 1.f, a2, s); });
+      op([=](cudaStream_t s) { return pose_conv_run(a1, PB, 16, Hs / 2, Ws / 2, pw.conv[2].w, pw.conv[2].b, 16, 3, 1, a2, s); });
       release(a1);
       bf16* a3 = alloc(static_cast<size_t>(PB) * (Hs / 4) * (Ws / 4) * 32);
-      op([=](cudaStream_t s) { return direct_conv_run(a2, 0, PB, 16, Hs / 2, Ws / 2, pw.conv[3].w, pw.conv[3].b, 32, 4, 2, 1, 1.f, a3, s); });
+      op([=](cudaStream_t s) { return pose_conv_run(a2, PB, 16, Hs / 2, Ws / 2, pw.conv[3].w, pw.conv[3].b, 32, 4, 2, a3, s); });
       release(a2);
       bf16* a4 = alloc(static_cast<size_t>(PB) * (Hs / 4) * (Ws / 4) * 32);
-      op([=](cudaStream_t s) { return direct_conv_run(a3, 0, PB, 32, Hs / 4, Ws / 4, pw.conv[4].w, pw.conv[4].b, 32, 3, 1, 1, 1.f, a4, s); });
+      op([=](cudaStream_t s) { return pose_conv_run(a3, PB, 32, Hs / 4, Ws / 4, pw.conv[4].w, pw.conv[4].b, 32, 3, 1, a4, s); });
       release(a3);
       bf16* col = alloc(static_cast<size_t>(PM0) * 512);
       op([=](cudaStream_t s) { return im2col_nhwc_run(a4, PB, Hs / 4, Ws / 4, 32, 4, 2, col, s); });
