@@ -63,8 +63,9 @@ struct TileCoord {
   int pa, pb;      // conv, n_phases == 4: sub-pixel phase of this tile (0 otherwise)
 };
 
+template <bool kConv>
 __device__ __forceinline__ void tile_coords(const GemmKernelArgs& a, int m_tile, TileCoord& t) {
-  if (a.mode == 0) {
+  if (!kConv) {
     t.m0 = m_tile * BLOCK_M;
     t.n_img0 = t.y0 = t.x0 = 0;
     t.pa = t.pb = 0;
@@ -122,7 +123,15 @@ __device__ __forceinline__ float colsum16(float (&v)[16], int lane) {
   return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
 }
 
-template <bool kGeglu>
+// Epilogue feature bits of the kernel template: a CLEAR bit compiles the feature out, a set bit is still checked at run
+// time.  The epilogue runs 12 warps x (block_n / 16) chunks per tile and, for the short-K projections, is what bounds the
+// kernel; with every feature behind a run-time flag a 16-column chunk cost ~140 instructions (uniform loads, tests and
+// branches around ~30 of real work; ncu source counters, profiles/README.md).  gemm_run picks the instantiation whose bits
+// equal the launch's features, or the E_ALL one.
+enum : int { E_BIAS = 1, E_ROWVEC = 2, E_ACT = 4, E_RES = 8, E_STATS = 16, E_KV = 32, E_ALL = 63 };
+
+// kConv: implicit-GEMM conv loader / output mapping (a.mode == 1); kTma: TMA-store epilogue (a.tma_store)
+template <bool kGeglu, bool kConv, bool kTma, int kEpi>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_a2,
                  const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_out,
@@ -182,7 +191,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const int m_tile = tile / a.n_tiles;
       const int n_tile = tile % a.n_tiles;
       TileCoord tc;
-      tile_coords(a, m_tile, tc);
+      tile_coords<kConv>(a, m_tile, tc);
       const int n0 = n_tile * a.block_n;
       for (int kb = 0; kb < a.k_blocks; ++kb) {
         mbar_wait(&empty[stage], phase ^ 1);
@@ -190,7 +199,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         uint8_t* sb = sa + A_BYTES;
         if (D4D_DBG(a, 1)) {  // ablation: no loads (tools build only)
           if (elect_one()) mbar_arrive(&full[stage]);
-        } else if (a.mode == 0) {
+        } else if (!kConv) {
           const bool first = kb < a.kb_split;
           const int ka = first ? kb * BLOCK_K : (kb - a.kb_split) * BLOCK_K;
           if (elect_one()) {
@@ -270,7 +279,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const int t_piece = lane & 3;
     auto chunk_at = [&](int k) { return 2 * (unit0 + EPI_WARPS_PER_QUARTER * (k >> 1)) + (k & 1); };
     auto row_of = [&](const TileCoord& tc, int rr, long long& row, int& img, bool& valid) {
-      if (a.mode == 0) {
+      if (!kConv) {
         row = static_cast<long long>(tc.m0) + rr;
         valid = row < a.M;
         img = a.rows_per_image > 0 ? static_cast<int>(row / a.rows_per_image) : 0;
@@ -298,7 +307,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const int m_tile = tile / a.n_tiles;
       const int n_tile = tile % a.n_tiles;
       TileCoord tc;
-      tile_coords(a, m_tile, tc);
+      tile_coords<kConv>(a, m_tile, tc);
       const int n0 = n_tile * a.block_n;
 
       long long row;  // output row (pixel/token index) of this thread's accumulator row
@@ -308,20 +317,23 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       // rows this lane writes in the transposed (coalesced) store
       long long t_row[4];
       bool t_valid[4];
+      auto calc_t_rows = [&]() {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        int img_unused;
-        row_of(tc, q * 32 + i * 8 + (lane >> 2), t_row[i], img_unused, t_valid[i]);
-      }
+        for (int i = 0; i < 4; ++i) {
+          int img_unused;
+          row_of(tc, q * 32 + i * 8 + (lane >> 2), t_row[i], img_unused, t_valid[i]);
+        }
+      };
+      if (!kTma) calc_t_rows();  // (TMA-store kernels need them only for an odd last 16-column chunk: computed there)
       // flush one staged unit: `pieces` = 2 (one 16-column chunk) or 4; ocol = first output column of the unit
       auto flush = [&](int pieces, int ocol) {
-        if (a.tma_store && pieces == 4) {
+        if (kTma && pieces == 4) {
           // the staged [32 rows][32 columns] unit is the source box of one TMA store (rows / columns outside the tensor
           // are clipped by the tensor map); the other staging buffer takes the next unit while this one is being read
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0 && !D4D_DBG(a, 32)) {
-            if (a.mode == 0) {
+            if (!kConv) {
               tma_store_2d(&tmap_out, stg, ocol, tc.m0 + q * 32);
             } else {
               const int r2 = (q * 32) / a.BW;
@@ -341,6 +353,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           return;
         }
         __syncwarp();
+        if (kTma) calc_t_rows();
         uint4 t[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -364,12 +377,15 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       // L2/HBM latency overlaps the TMEM load and the math; bias (L1-resident broadcast) is loaded under the wait.
       if (!kGeglu) {
         const int chunks = a.block_n / 16;
-        const bool direct = a.kv_world > 0;  // fused K/V scatter keeps the direct row-wise stores
+        const bool direct = (kEpi & E_KV) && a.kv_world > 0;  // fused K/V scatter keeps the direct row-wise stores
+        const bool has_bias = (kEpi & E_BIAS) && a.bias != nullptr, has_rv = (kEpi & E_ROWVEC) && a.rowvec != nullptr;
+        const bool has_res = (kEpi & E_RES) && a.residual != nullptr, has_stats = (kEpi & E_STATS) && a.stats != nullptr;
+        const bool has_act = (kEpi & E_ACT) && a.act == 1, has_scale = (kEpi & E_ACT) && a.out_scale != 1.0f;
         const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
         uint4 r0 = z4, r1 = z4, v0 = z4, v1 = z4, nr0 = z4, nr1 = z4, nv0 = z4, nv1 = z4;
-        const bf16* res_row = a.residual ? a.residual + static_cast<size_t>(row) * a.ld_res + n0 : nullptr;
-        const bf16* rv_row = a.rowvec ? a.rowvec + static_cast<size_t>(img) * a.ld_rowvec + n0 : nullptr;
-        const bool ld_res = valid && res_row != nullptr && !D4D_DBG(a, 64), ld_rv = valid && rv_row != nullptr;
+        const bf16* res_row = has_res ? a.residual + static_cast<size_t>(row) * a.ld_res + n0 : nullptr;
+        const bf16* rv_row = has_rv ? a.rowvec + static_cast<size_t>(img) * a.ld_rowvec + n0 : nullptr;
+        const bool ld_res = valid && has_res && !D4D_DBG(a, 64), ld_rv = valid && has_rv;
         if (chunk_at(0) < chunks) {
           const int c0 = chunk_at(0);
           if (ld_res) {  // plain loads: the residual may alias the output (in-place add)
@@ -399,14 +415,14 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             }
           }
           float4 b4[4];
-          if (a.bias) {
+          if (has_bias) {
             const float4* bp = reinterpret_cast<const float4*>(a.bias + col);
 #pragma unroll
             for (int i = 0; i < 4; ++i) b4[i] = __ldg(bp + i);
           }
           tmem_ld_wait();
           float sv[16];  // stats: the rounded outputs of this thread's row (zero for rows outside the tensor)
-          if (a.stats) {
+          if (has_stats) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) sv[i] = 0.f;
           }
@@ -414,23 +430,23 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             float f[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
-            if (a.bias) {
+            if (has_bias) {
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 f[4 * i] += b4[i].x; f[4 * i + 1] += b4[i].y; f[4 * i + 2] += b4[i].z; f[4 * i + 3] += b4[i].w;
               }
             }
-            if (a.rowvec) { add8_bf16(f, v0); add8_bf16(f + 8, v1); }
-            if (a.act == 1) {
+            if (has_rv) { add8_bf16(f, v0); add8_bf16(f + 8, v1); }
+            if (has_act) {
 #pragma unroll
               for (int i = 0; i < 16; ++i) f[i] = silu_f(f[i]);
             }
-            if (a.out_scale != 1.0f) {
+            if (has_scale) {
 #pragma unroll
               for (int i = 0; i < 16; ++i) f[i] *= a.out_scale;
             }
-            if (a.residual) { add8_bf16(f, r0); add8_bf16(f + 8, r1); }
-            if (a.stats) {  // statistics of what is stored: round to bf16 first
+            if (has_res) { add8_bf16(f, r0); add8_bf16(f + 8, r1); }
+            if (has_stats) {  // statistics of what is stored: round to bf16 first
 #pragma unroll
               for (int i = 0; i < 16; ++i) sv[i] = f[i] = __bfloat162float(__float2bfloat16_rn(f[i]));
             }
@@ -459,7 +475,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               op[1] = o1;
             }
           }
-          if (a.stats) {
+          if (has_stats) {
             // GroupNorm statistics of the output: column sums over this warp's 32 rows (they belong to ONE image:
             // gemm_prepare checks it), one red.global per (column, moment) and warp.  Lane 0 holds the first row / the
             // tile's minimal (x, y): when it is outside the tensor the whole warp is.
@@ -468,7 +484,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             for (int i = 0; i < 16; ++i) sq[i] = sv[i] * sv[i];
             const float cs = colsum16(sv, lane), cq = colsum16(sq, lane);
             const int cc = ((lane & 16) ? 8 : 0) + ((lane & 8) ? 4 : 0) + ((lane & 4) ? 2 : 0) + ((lane & 2) ? 1 : 0);
-            const int img0 = __shfl_sync(0xffffffffu, a.mode == 0 ? static_cast<int>(row / a.stats_rows) : img, 0);
+            const int img0 = __shfl_sync(0xffffffffu, !kConv ? static_cast<int>(row / a.stats_rows) : img, 0);
             if (__shfl_sync(0xffffffffu, valid ? 1 : 0, 0)) {
               const long long fx = __float2ll_rn((lane & 1) ? cq * kGnSqScale : cs * kGnSumScale);  // fixed point: order-free
               atomicAdd(reinterpret_cast<unsigned long long*>(a.stats) + (static_cast<size_t>(img0) * a.N + col + cc) * 2 + (lane & 1),
@@ -483,6 +499,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         // n_tile*block_n/2 .. +block_n/2
         const int half = a.block_n / 2;
         const int chunks = half / 16;
+        const bool has_bias = (kEpi & E_BIAS) && a.bias != nullptr;
         for (int k = 0;; ++k) {
           const int c = chunk_at(k);
           if (c >= chunks) break;
@@ -490,7 +507,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           tmem_ld16(taddr + c * 16, va);
           tmem_ld16(taddr + half + c * 16, vg);
           float4 ba[4], bg[4];
-          if (a.bias) {
+          if (has_bias) {
             const float4* pa = reinterpret_cast<const float4*>(a.bias + n0 + c * 16);
             const float4* pg = reinterpret_cast<const float4*>(a.bias + n0 + half + c * 16);
 #pragma unroll
@@ -505,7 +522,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               uint64_t a23 = f2_pack(__uint_as_float(va[4 * i + 2]), __uint_as_float(va[4 * i + 3]));
               uint64_t g01 = f2_pack(__uint_as_float(vg[4 * i]), __uint_as_float(vg[4 * i + 1]));
               uint64_t g23 = f2_pack(__uint_as_float(vg[4 * i + 2]), __uint_as_float(vg[4 * i + 3]));
-              if (a.bias) {
+              if (has_bias) {
                 a01 = f2_add(a01, f2_pack(ba[i].x, ba[i].y));
                 a23 = f2_add(a23, f2_pack(ba[i].z, ba[i].w));
                 g01 = f2_add(g01, f2_pack(bg[i].x, bg[i].y));
@@ -519,7 +536,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             o0.z = pack_bf16x2(o[4], o[5]);   o0.w = pack_bf16x2(o[6], o[7]);
             o1.x = pack_bf16x2(o[8], o[9]);   o1.y = pack_bf16x2(o[10], o[11]);
             o1.z = pack_bf16x2(o[12], o[13]); o1.w = pack_bf16x2(o[14], o[15]);
-            if (a.tma_store) {
+            if (kTma) {
               stage_half(k & 1, o0, o1);  // staged unit -> one TMA store (the one-MUFU GELU left the stores as the bound)
             } else if (!D4D_DBG(a, 32)) {  // direct row-wise stores
               uint4* op = reinterpret_cast<uint4*>(a.out + static_cast<size_t>(row) * a.ldo + n_tile * half + c * 16);
@@ -527,7 +544,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               op[1] = o1;
             }
           }
-          if (a.tma_store && ((k & 1) || c + 1 >= chunks)) flush((k & 1) ? 4 : 2, n_tile * half + (c & ~1) * 16);
+          if (kTma && ((k & 1) || c + 1 >= chunks)) flush((k & 1) ? 4 : 2, n_tile * half + (c & ~1) * 16);
         }
       }
       tc_fence_before();
@@ -706,15 +723,61 @@ int gemm_prepare(const GemmDesc& d, GemmLaunch* L) {
   return 0;
 }
 
-int gemm_run(const GemmLaunch& L, cudaStream_t stream) {
-  static PerDeviceOnce attr_once[2];
-  if (L.args.geglu) {
-    if (int rc = ensure_dyn_smem(gemm_umma_kernel<true>, SMEM_BYTES, attr_once[1])) return rc;
-    D4D_CUDA_OK(launch_pdl(gemm_umma_kernel<true>, dim3(L.grid), dim3(NUM_THREADS), SMEM_BYTES, stream, L.tmap_a, L.tmap_a2, L.tmap_b, L.tmap_out, L.args));
-  } else {
-    if (int rc = ensure_dyn_smem(gemm_umma_kernel<false>, SMEM_BYTES, attr_once[0])) return rc;
-    D4D_CUDA_OK(launch_pdl(gemm_umma_kernel<false>, dim3(L.grid), dim3(NUM_THREADS), SMEM_BYTES, stream, L.tmap_a, L.tmap_a2, L.tmap_b, L.tmap_out, L.args));
+namespace {
+
+using GemmKernelFn = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const GemmKernelArgs);
+struct GemmVariant {
+  bool geglu, conv, tma;
+  int epi;
+  GemmKernelFn fn;
+};
+#define D4D_GV(G, C, T, E) {G, C, T, E, gemm_umma_kernel<G, C, T, E>}
+// the feature sets the UNet plan launches (csrc/unet.cu), plus one E_ALL kernel per (conv, tma) pair for everything else
+const GemmVariant kGemmVariants[] = {
+    // plain GEMM, TMA-store epilogue (k_blocks <= 24): qkv | proj_in, shortcut | attn out, ff2 | proj_out, conv_in
+    D4D_GV(false, false, true, 0), D4D_GV(false, false, true, E_BIAS), D4D_GV(false, false, true, E_BIAS | E_RES),
+    D4D_GV(false, false, true, E_BIAS | E_RES | E_STATS), D4D_GV(false, false, true, E_ALL),
+    // plain GEMM, row-segment stores (long K): ff2
+    D4D_GV(false, false, false, E_BIAS | E_RES), D4D_GV(false, false, false, E_ALL),
+    // 3x3 convs (long K: row-segment stores): resnet conv1 | conv2 | down / up sampling
+    D4D_GV(false, true, false, E_BIAS | E_ROWVEC | E_STATS), D4D_GV(false, true, false, E_BIAS | E_RES | E_STATS),
+    D4D_GV(false, true, false, E_BIAS | E_STATS), D4D_GV(false, true, false, E_ALL), D4D_GV(false, true, true, E_ALL),
+    // GEGLU projection (only the bias bit matters)
+    D4D_GV(true, false, true, E_BIAS), D4D_GV(true, false, false, E_BIAS),
+};
+#undef D4D_GV
+constexpr int kNumGemmVariants = sizeof(kGemmVariants) / sizeof(kGemmVariants[0]);
+
+int gemm_variant_of(const GemmKernelArgs& a) {
+  const bool conv = a.mode != 0, tma = a.tma_store != 0, geglu = a.geglu != 0;
+  int need = 0;
+  if (a.bias) need |= E_BIAS;
+  if (!geglu) {
+    if (a.rowvec) need |= E_ROWVEC;
+    if (a.act == 1 || a.out_scale != 1.0f) need |= E_ACT;
+    if (a.residual) need |= E_RES;
+    if (a.stats) need |= E_STATS;
+    if (a.kv_world > 0) need |= E_KV;
   }
+  int generic = -1;
+  for (int i = 0; i < kNumGemmVariants; ++i) {
+    const GemmVariant& v = kGemmVariants[i];
+    if (v.geglu != geglu || v.conv != conv || v.tma != tma) continue;
+    if (v.epi == need) return i;
+    if ((v.epi & need) == need && (generic < 0 || v.epi == E_ALL)) generic = i;  // geglu: E_BIAS covers {} as well
+  }
+  return generic;
+}
+
+}  // namespace
+
+int gemm_run(const GemmLaunch& L, cudaStream_t stream) {
+  static PerDeviceOnce attr_once[kNumGemmVariants];
+  const int vi = gemm_variant_of(L.args);
+  D4D_REQUIRE(vi >= 0, "no GEMM kernel instantiation covers this launch");
+  const GemmVariant& v = kGemmVariants[vi];
+  if (int rc = ensure_dyn_smem(v.fn, SMEM_BYTES, attr_once[vi])) return rc;
+  D4D_CUDA_OK(launch_pdl(v.fn, dim3(L.grid), dim3(NUM_THREADS), SMEM_BYTES, stream, L.tmap_a, L.tmap_a2, L.tmap_b, L.tmap_out, L.args));
   D4D_CUDA_OK(cudaGetLastError());
   return 0;
 }
