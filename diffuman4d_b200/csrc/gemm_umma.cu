@@ -37,20 +37,25 @@ constexpr int SMEM_BYTES = 227 * 1024;             // everything an SM has: the 
 // GEMMs); staged through shared memory the warp stores 8 rows x 64 contiguous bytes per instruction.
 // With TMA stores the staged unit IS the source box of a cp.async.bulk.tensor store (the staging swizzle below is the
 // 64-byte TMA swizzle), double-buffered per warp so that one store can still be reading while the next unit is staged.
-// Only short-K launches (k_blocks <= 20: the store-bound projections) with tiles up to 160 columns get the second staging
-// buffer: it costs a ring stage, and for long main loops the ring depth is what matters (measured: +4 % on the K >= 2560
-// GEMMs / convs with the smaller ring, profiles/README.md).
+// Only the shortest main loops (K = 320: k_blocks <= 5) get the second staging buffer: it costs a ring stage, and from
+// K = 640 on the ring depth matters more than the overlapped store (measured per shape with D4D_GEMM_STG_BUFS in the tools
+// build: K = 320 -1..-3 %, K = 640 +5 %, K = 1280 +8 % with two buffers; profiles/README.md).
 constexpr int STG_WARP_BYTES = 32 * 64;
 constexpr int STG_BYTES1 = 4 * EPI_WARPS_PER_QUARTER * STG_WARP_BYTES;  // 24 KB per set of staging buffers
-__host__ __device__ inline int stg_bufs_for(int block_n, int k_blocks) { return (block_n > 160 || k_blocks > 20) ? 1 : 2; }
-__host__ __device__ inline int ring_bytes_for(int block_n, int k_blocks) {
-  return SMEM_BYTES - 1024 /*align*/ - BAR_BYTES - STG_BYTES1 * stg_bufs_for(block_n, k_blocks);
+inline int stg_bufs_for(int block_n, int k_blocks) {
+#ifdef D4D_ABLATE
+  if (const char* e = getenv("D4D_GEMM_STG_BUFS")) return atoi(e) == 2 ? 2 : 1;  // tools build: A/B the rule below
+#endif
+  return k_blocks <= 5 ? 2 : 1;
+}
+__host__ __device__ inline int ring_bytes_for(int stg_bufs) {
+  return SMEM_BYTES - 1024 /*align*/ - BAR_BYTES - STG_BYTES1 * stg_bufs;
 }
 // The main loop is bound by the latency of the TMA loads in flight (measured: ~650-700 cycles per k-block whatever block_n
 // is, with 4 x 48 KB stages), so the ring depth follows the tile width: 4 stages at block_n 256 ... 8 at block_n <= 96.
 __host__ __device__ inline int stage_bytes_for(int block_n) { return A_BYTES + block_n * BLOCK_K * 2; }
-__host__ __device__ inline int stages_for(int block_n, int k_blocks) {
-  const int s = ring_bytes_for(block_n, k_blocks) / stage_bytes_for(block_n);
+__host__ __device__ inline int stages_for(int block_n, int stg_bufs) {
+  const int s = ring_bytes_for(stg_bufs) / stage_bytes_for(block_n);
   return s > MAX_STAGES ? MAX_STAGES : s;
 }
 constexpr int NUM_THREADS = 64 + 128 * EPI_WARPS_PER_QUARTER;  // warp0 TMA, warp1 MMA(+TMEM alloc), then the epilogue warps
@@ -141,12 +146,12 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
   uint8_t* staging = smem + BAR_BYTES;
-  const int STG_BUFS = stg_bufs_for(a.block_n, a.k_blocks);
+  const int STG_BUFS = a.stg_bufs;
   smem += BAR_BYTES + STG_BYTES1 * STG_BUFS;
   uint64_t* full = bars;                   // [MAX_STAGES]
   uint64_t* empty = bars + MAX_STAGES;     // [MAX_STAGES]
   uint64_t* tfull = bars + 2 * MAX_STAGES; // [2]
-  const int STAGES = stages_for(a.block_n, a.k_blocks);
+  const int STAGES = stages_for(a.block_n, a.stg_bufs);
   const int STAGE_BYTES = stage_bytes_for(a.block_n);
   uint64_t* tempty = tfull + 2;        // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
@@ -715,6 +720,7 @@ int gemm_prepare(const GemmDesc& d, GemmLaunch* L) {
       }
     }
   }
+  a.stg_bufs = stg_bufs_for(bn, a.k_blocks);
   int dev = 0, sms = 0;
   D4D_CUDA_OK(cudaGetDevice(&dev));
   D4D_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));

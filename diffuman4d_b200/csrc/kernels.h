@@ -41,6 +41,7 @@ struct GemmKernelArgs {
   int ldo;
   int geglu;
   int tma_store;    // 1: 32-row x 32-column epilogue units leave through TMA stores (tmap_out) instead of st.global
+  int stg_bufs;     // staging buffers per epilogue warp (1 or 2; the second one costs a ring stage, gemm_umma.cu)
   int act;          // 0 none, 1 SiLU applied to (acc + bias + rowvec) before scale/residual
   float out_scale;  // multiplies (acc + bias + rowvec) after the activation
   // fused GroupNorm statistics of the OUTPUT tensor: per (image, column) sum and sum of squares in 64-bit FIXED POINT
