@@ -380,6 +380,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
       // Residual / row-vector loads of the next chunk are issued before the TMEM wait of the current one so that their
       // L2/HBM latency overlaps the TMEM load and the math; bias (L1-resident broadcast) is loaded under the wait.
+      // (Fetching the residual two chunks ahead measured no better: 74 vs 69 us on the L0 projection.)
       if (!kGeglu) {
         const int chunks = a.block_n / 16;
         const bool direct = (kEpi & E_KV) && a.kv_world > 0;  // fused K/V scatter keeps the direct row-wise stores
@@ -585,12 +586,19 @@ int gemm_prepare(const GemmDesc& d, GemmLaunch* L) {
     const long long m_tiles_est = (rows + BLOCK_M - 1) / BLOCK_M;
     const int mult = d.geglu ? 32 : 16;
     bn = gemm_pick_block_n(d.N, mult);
+    // K <= 320 (5 k-blocks): the epilogue, not the main loop, paces the tile, and its length is the number of 16-column
+    // chunks of the busiest of the 3 warps of a TMEM lane quarter (32-column units dealt round-robin): 6 at block_n 240,
+    // 4 at 192 or 160 (measured: L0 qkv 97 us at 240, 94 us at 192, profiles/r02b_tune_block_n.txt)
+    const int kb_est = d.conv ? 9 * ((d.Cin + BLOCK_K - 1) / BLOCK_K) : (d.K1 + (d.A2 ? d.K2 : 0) + BLOCK_K - 1) / BLOCK_K;
+    const bool epilogue_paced = !d.geglu && kb_est <= 5;
     long long best_cost = -1;
     for (int c = mult; c <= 256; c += mult) {
       if (d.N % c != 0 || (c < 64 && c != bn)) continue;
       const long long tiles = m_tiles_est * (d.N / c);
       const long long waves = (tiles + sms0 - 1) / sms0;
-      const long long cost = waves * (c + 48);
+      const int chunks = c / 16, units = (chunks + 1) / 2;
+      const int busiest = 2 * ((units + EPI_WARPS_PER_QUARTER - 1) / EPI_WARPS_PER_QUARTER);  // chunks of warp 0 (upper bound)
+      const long long cost = waves * ((epilogue_paced ? 40 * (busiest < chunks ? busiest : chunks) : c) + 48);
       if (best_cost < 0 || cost < best_cost || (cost == best_cost && c > bn)) { best_cost = cost; bn = c; }
     }
   }
