@@ -268,13 +268,18 @@ inline int ensure_dyn_smem(F func, int bytes, PerDeviceOnce& once) {
 
 // Programmatic dependent launch: the kernel may become resident while its predecessor in the stream drains; it must
 // execute pdl_wait() (common.cuh) before touching anything a predecessor wrote.  Measured on the W16 step: 46.63 ms with the
-// attribute vs 46.55 ms without (the kernels are long enough that launch gaps do not show), so it is opt-in: D4D_PDL=1.
+// attribute vs 46.55 ms without (the kernels are long enough that launch gaps do not show), so the product library leaves
+// it off; the tools build (libd4d_test.so) turns it on with D4D_PDL=1.
 inline bool pdl_enabled() {
+#ifdef D4D_ABLATE
   static const bool on = [] {
     const char* e = getenv("D4D_PDL");
     return e && e[0] == '1';
   }();  // thread-safe one-time initialisation
   return on;
+#else
+  return false;
+#endif
 }
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
