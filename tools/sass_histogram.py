@@ -1,6 +1,7 @@
 """SASS opcode histogram of the shipped product library (cuobjdump -sass): the Blackwell-native evidence the profiling
 recipe asks for (UTC*MMA = tcgen05.mma, LDTM/STTM = tcgen05.ld/st, UTMALDG/UTMASTG = TMA, UTCBAR = tcgen05.commit) and a
-check that no legacy tensor path (HMMA / HGMMA) is present.  Usage: python tools/sass_histogram.py > profiles/rNN_sass_histogram.txt"""
+check of where the warp-level tensor path is used: HMMA (mma.sync) appears only in the four pose-encoder convs whose 16 / 32
+output channels are too narrow for a tcgen05 tile (csrc/elementwise.cu); HGMMA nowhere.  Usage: python tools/sass_histogram.py > profiles/rNN_sass_histogram.txt"""
 import collections
 import os
 import re
