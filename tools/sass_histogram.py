@@ -46,4 +46,4 @@ print("\n# whole library")
 for x in sorted(tot, key=lambda s: s.strip()):
     if not x.startswith("  "):
         print(f"    {x:<34}{tot[x]:>6}")
-print(f"    legacy tensor path (HMMA/HGMMA): {tot.get('HMMA', 0) + tot.get('HGMMA', 0)}")
+print(f"    warp-level mma.sync (HMMA; pose-encoder convs only) / HGMMA: {tot.get('HMMA', 0) + tot.get('HGMMA', 0)}")
