@@ -196,3 +196,27 @@ def test_plucker_embeds_match_reference_ray_utils():
     rel = relative_poses(g["c2w"])
     torch.testing.assert_close(rel, g["rel_poses"], rtol=1e-5, atol=1e-6)
     torch.testing.assert_close(plucker_embeds(16, 16, g["K"], rel), g["plucker_rel"], rtol=1e-5, atol=5e-6)
+
+
+def test_upsample_phase_weights_reproduce_nearest2x_conv3x3():
+    """The sub-pixel form the Upsample2D kernel executes (conv_kind 2 / 3, csrc/gemm_umma.cu) is an identity, not an
+    approximation: with integer-valued inputs and weights (exact in bf16 and in the fp32 sums) the four 2x2 phase convs
+    on the low-resolution tensor equal `F.interpolate(nearest, x2)` + 3x3 / pad 1 conv bit for bit (reference:
+    diffusers Upsample2D as called at unet_multiview_blocks.py:620)."""
+    import torch.nn.functional as F
+    from diffuman4d_b200.ops import upsample_phase_weights
+    g = torch.Generator().manual_seed(0)
+    n, cin, cout, H, W = 2, 5, 3, 6, 7
+    x = torch.randint(-4, 5, (n, cin, H, W), generator=g).float()
+    w = torch.randint(-3, 4, (cout, cin, 3, 3), generator=g).float()
+    ref = F.conv2d(F.interpolate(x, scale_factor=2, mode="nearest"), w, padding=1)
+    phases = upsample_phase_weights(w)                       # [a*2+b] -> [Cout, 4 (ty*2+tx), Cin] bf16
+    out = torch.zeros_like(ref)
+    xp = F.pad(x, (1, 1, 1, 1))
+    for a in range(2):
+        for b in range(2):
+            wp = phases[a * 2 + b].float().view(cout, 2, 2, cin).permute(0, 3, 1, 2)     # OIHW 2x2
+            # rows {-1, 0} for a = 0, {0, +1} for a = 1 (columns alike): a window of the padded input
+            y = F.conv2d(xp[:, :, a:a + H + 1, b:b + W + 1], wp)
+            out[:, :, a::2, b::2] = y
+    assert torch.equal(out, ref)
