@@ -83,20 +83,6 @@ __global__ void im2col_nhwc_kernel(const bf16* __restrict__ x, int n, int H, int
   *reinterpret_cast<uint4*>(out + (r * kk + tap) * C + o8 * 8) = v;
 }
 
-__global__ void upsample2x_kernel(const bf16* __restrict__ x, int n, int H, int W, int C, bf16* __restrict__ out) {
-  const int oct = C / 8;
-  const long long total = static_cast<long long>(n) * (2 * H) * (2 * W) * oct;
-  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int o8 = static_cast<int>(idx % oct);
-  long long r = idx / oct;
-  const int xo = static_cast<int>(r % (2 * W));
-  const int yo = static_cast<int>((r / (2 * W)) % (2 * H));
-  const int img = static_cast<int>(r / (static_cast<long long>(4) * W * H));
-  const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + ((static_cast<size_t>(img) * H + yo / 2) * W + xo / 2) * C + o8 * 8));
-  *reinterpret_cast<uint4*>(out + r * C + o8 * 8) = v;
-}
-
 // [n*H*W, ld] (first C columns) -> NCHW [n, C, H, W]
 __global__ void nhwc_to_nchw_kernel(const bf16* __restrict__ x, int ld, int n, int C, int hw, bf16* __restrict__ out) {
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -331,16 +317,6 @@ __global__ void fill_bf16_kernel(bf16* __restrict__ p, long long n, float v) {
     p[i] = b;
 }
 
-__global__ void cfg_skeleton_kernel(const bf16* __restrict__ skel, long long per_frame, int F, bf16* __restrict__ out) {
-  const long long total = per_frame * F;
-  const bf16 mone = __float2bfloat16_rn(-1.f);
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    out[i] = mone;
-    out[total + i] = skel[i];
-  }
-}
-
 // ---------------------------------------------------------------------------------------------
 // a-13 + a-14: CFG combine + per-frame DDIM step (pipeline_diffuman4d.py:408-423, upstream DDIMScheduler.step)
 // ---------------------------------------------------------------------------------------------
@@ -466,14 +442,6 @@ int im2col_nhwc_run(const bf16* x, int n, int H, int W, int C, int ksize, int st
   return 0;
 }
 
-int upsample2x_run(const bf16* x, int n, int H, int W, int C, bf16* out, cudaStream_t stream) {
-  D4D_REQUIRE(C % 8 == 0, "upsample channels");
-  const long long total = static_cast<long long>(n) * 4 * H * W * (C / 8);
-  upsample2x_kernel<<<blocks_for(total, 256), 256, 0, stream>>>(x, n, H, W, C, out);
-  D4D_CUDA_OK(cudaGetLastError());
-  return 0;
-}
-
 int nhwc_to_nchw_run(const bf16* x, int ld, int n, int C, int hw, bf16* out, cudaStream_t stream) {
   const long long total = static_cast<long long>(n) * C * hw;
   nhwc_to_nchw_kernel<<<blocks_for(total, 256), 256, 0, stream>>>(x, ld, n, C, hw, out);
@@ -546,15 +514,6 @@ int broadcast_neg_images_run(const bf16* small, long long per_img, int F, bf16* 
 }
 int fill_bf16_run(bf16* p, long long n, float v, cudaStream_t stream) {
   fill_bf16_kernel<<<148 * 4, 256, 0, stream>>>(p, n, v);
-  D4D_CUDA_OK(cudaGetLastError());
-  return 0;
-}
-
-int cfg_skeleton_run(const bf16* skel, long long per_frame_elems, int F, bf16* out, cudaStream_t stream) {
-  const long long total = per_frame_elems * F;
-  long long nb = (total + 255) / 256;
-  const int blocks = static_cast<int>(nb < 148 * 16 ? nb : 148 * 16);
-  cfg_skeleton_kernel<<<blocks, 256, 0, stream>>>(skel, per_frame_elems, F, out);
   D4D_CUDA_OK(cudaGetLastError());
   return 0;
 }

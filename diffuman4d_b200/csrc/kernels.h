@@ -172,8 +172,6 @@ int pose_conv0_run(const bf16* x_nchw, int n, int H, int W, const bf16* w, const
 // pose encoder layers 1-4 on mma.sync: NHWC in / out, pad 1 + SiLU; w [Cout][k*k*Cin + 8] (K index = tap*Cin + c, zero pad)
 int pose_conv_run(const bf16* x, int n, int Cin, int H, int W, const bf16* w, const float* bias, int Cout, int ksize,
                   int stride, bf16* out_nhwc, cudaStream_t stream);
-// nearest x2 upsample NHWC
-int upsample2x_run(const bf16* x, int n, int H, int W, int C, bf16* out, cudaStream_t stream);
 // generic NHWC im2col, pad 1: [n,H,W,C] -> [n*Ho*Wo, k*k*C]
 int im2col_nhwc_run(const bf16* x, int n, int H, int W, int C, int ksize, int stride, bf16* out, cudaStream_t stream);
 
@@ -192,8 +190,6 @@ struct AssembleArgs {
   long long* timestep_out;  // out [(cfg?2:1)*F]
 };
 int assemble_input_run(const AssembleArgs& a, cudaStream_t stream);
-// CFG-negative skeleton batch for the pose encoder: out[0:F] = -1, out[F:2F] = skeletons
-int cfg_skeleton_run(const bf16* skel, long long per_frame_elems, int F, bf16* out, cudaStream_t stream);
 
 // a-13 + a-14: CFG combine + per-frame DDIM step (pipeline_diffuman4d.py:408-423)
 struct DdimArgs {
