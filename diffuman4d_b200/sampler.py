@@ -20,9 +20,19 @@ The dataset object supplies ``scene_label`` and ``get_item(scene_label, spa_labe
 like the reference's ``SpaTemDataset`` (src/data/spatem_dataset.py:76-212); pipelines supply
 ``sliding_iterative_denoise(**kwargs) -> {"images", "latents", "timestep_indices", "fully_denoised"}`` (PIPE:439-559), e.g.
 ``B200Diffuman4DPipeline``.
+
+Input prefetch and asynchronous output (both opt-in): in the reference every worker thread runs
+``dataset.get_item`` (PIL decode, crop, bicubic resize, composite, Pluecker rays: CPU work) -> denoise ->
+``save_sampling_results`` (webp grid + per-image JPEG, src/samplers/utils/sampling_utils.py:54-114) strictly in sequence, so
+the GPU idles during both.  With ``prefetch=True`` the dataset part of the NEXT task of the round is loaded by a helper
+thread while the current task is on the GPU (the tasks of a round touch disjoint target cells, and the grid rows of a task
+are still gathered on the calling thread right before its denoise); with ``async_save=True`` ``save_fn`` runs on one
+worker thread in task order behind a bounded queue and its first exception is re-raised by ``execute_tasks``.
 """
 from __future__ import annotations
 
+import queue
+import threading
 from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -37,8 +47,10 @@ class B200SlidingIterativeSampler:
                  spa_label_range: Optional[List[int]] = (0, 48, 1), tem_label_range: Optional[List[int]] = (0, 150, 1),
                  spa_labels: Optional[Sequence[int]] = None, tem_labels: Optional[Sequence[int]] = None,
                  input_spa_labels: Sequence[int] = (1, 13, 25, 37),
-                 save_fn: Optional[Callable[[dict, Optional[str]], None]] = None):
+                 save_fn: Optional[Callable[[dict, Optional[str]], None]] = None, prefetch: bool = False,
+                 async_save: bool = False):
         self.dataset, self.pipelines, self.output_dir, self.save_fn = dataset, list(pipelines), output_dir, save_fn
+        self.prefetch, self.async_save = prefetch, async_save
         self.window_size, self.sliding_stride, self.sliding_shift = window_size, sliding_stride, sliding_shift
         self.bidirectional, self.num_denoising_steps = bidirectional, num_denoising_steps
         self.alternation_rounds, self.guidance_scale = alternation_rounds, guidance_scale
@@ -106,6 +118,10 @@ class B200SlidingIterativeSampler:
 
     # ---- SAMP:102-153 -----------------------------------------------------------------------------------------
     def load_sample(self, alt: int, domain: str, domain_label: str) -> dict:
+        return self._attach_grid(self._fetch(alt, domain, domain_label))
+
+    def _fetch(self, alt: int, domain: str, domain_label: str) -> dict:
+        """The dataset half of SAMP:102-153 (host work only: safe on a helper thread)."""
         if domain == "spatial":
             spa_labels, tem_labels = self.spa_labels, [domain_label]
             input_indices = torch.tensor([self.spa_labels.index(label) for label in self.input_spa_labels])
@@ -125,7 +141,11 @@ class B200SlidingIterativeSampler:
         cond_masks[...] = 1.0
         cond_masks[input_indices, ...] = 0.0
         sample["cond_masks"] = cond_masks
+        return sample
 
+    def _attach_grid(self, sample: dict) -> dict:
+        """The grid half: this task's rows of the latent / timestep grid (reads what earlier ROUNDS wrote)."""
+        target_indices = sample["target_indices"]
         vi, ti = self._cells(sample["labels"])
         sample["_cells"] = (vi, ti)
         if self.grid_latents is None:
@@ -179,18 +199,29 @@ class B200SlidingIterativeSampler:
     def execute_tasks(self, rank: int = 0, world: int = 1, group=None, pipe_idx: int = 0):
         """All rounds.  ``world > 1`` (inside an initialised ``torch.distributed`` job): this rank runs its share of every
         round, then the ranks all-gather the cells they updated (the round barrier of RUN:53-55)."""
-        for tasks in self.all_tasks:
-            mine = shard_tasks(len(tasks), rank, world) if world > 1 else range(len(tasks))
-            keys, lats, tis = [], [], []
-            for i in mine:
-                sample = self.execute_one_task(tasks[i], pipe_idx=pipe_idx)
+        saver = _AsyncSaver(self.save_fn, self.output_dir) if (self.async_save and self.save_fn is not None) else None
+        try:
+            for tasks in self.all_tasks:
+                mine = list(shard_tasks(len(tasks), rank, world) if world > 1 else range(len(tasks)))
+                keys, lats, tis = [], [], []
+                fetched = _Prefetcher(self._fetch, [tasks[i] for i in mine]) if self.prefetch else None
+                for n, i in enumerate(mine):
+                    raw = fetched.get(n) if fetched is not None else self._fetch(**tasks[i])
+                    sample = self.denoise(self._attach_grid(raw), pipe_idx=pipe_idx)
+                    if saver is not None:
+                        saver.submit(sample)
+                    elif self.save_fn is not None:
+                        self.save_fn(sample, self.output_dir)
+                    if world > 1:
+                        vi, ti = sample["_cells"]
+                        keys += list(zip(vi.tolist(), ti.tolist()))
+                        lats.append(sample["result_latents"])
+                        tis.append(sample["timestep_indices"].to(torch.int64))
                 if world > 1:
-                    vi, ti = sample["_cells"]
-                    keys += list(zip(vi.tolist(), ti.tolist()))
-                    lats.append(sample["result_latents"])
-                    tis.append(sample["timestep_indices"].to(torch.int64))
-            if world > 1:
-                self._exchange(keys, lats, tis, group)
+                    self._exchange(keys, lats, tis, group)
+        finally:
+            if saver is not None:
+                saver.close()
 
     def _exchange(self, keys, lats, tis, group):
         if lats:
@@ -210,3 +241,72 @@ class B200SlidingIterativeSampler:
             self.grid_latents.index_put_((vi, tj), torch.stack([merged[c][0] for c in cells]).to(self.grid_latents.dtype))
             self.grid_timestep_indices.index_put_(
                 (vi, tj), torch.tensor([merged[c][1] for c in cells], dtype=torch.int64, device=self._grid_device))
+
+
+class _Prefetcher:
+    """Loads item n + 1 of a task list on a helper thread while the caller works on item n (depth 1: one sample of a
+    48-view task is ~0.6 GB of host tensors at 1024^2)."""
+
+    def __init__(self, fetch: Callable[..., dict], tasks: List[dict]):
+        self._fetch, self._tasks = fetch, tasks
+        self._next: Optional[Tuple[int, threading.Thread, list]] = None
+        self._start(0)
+
+    def _start(self, n: int):
+        if n >= len(self._tasks):
+            self._next = None
+            return
+        box: list = []
+
+        def run():
+            try:
+                box.append((True, self._fetch(**self._tasks[n])))
+            except BaseException as e:  # noqa: BLE001 -- handed to the consumer
+                box.append((False, e))
+        t = threading.Thread(target=run, name="d4d-prefetch", daemon=True)
+        t.start()
+        self._next = (n, t, box)
+
+    def get(self, n: int) -> dict:
+        assert self._next is not None and self._next[0] == n, "tasks are consumed in order"
+        _, t, box = self._next
+        t.join()
+        self._start(n + 1)
+        ok, val = box[0]
+        if not ok:
+            raise val
+        return val
+
+
+class _AsyncSaver:
+    """``save_fn(sample, output_dir)`` on one worker thread, in submission order, at most ``depth`` samples waiting.  The
+    first exception stops further saves and is re-raised by ``submit`` / ``close``."""
+
+    def __init__(self, save_fn: Callable[[dict, Optional[str]], None], output_dir: Optional[str], depth: int = 2):
+        self._save_fn, self._output_dir = save_fn, output_dir
+        self._q: "queue.Queue" = queue.Queue(maxsize=depth)
+        self._error: Optional[BaseException] = None
+        self._thread = threading.Thread(target=self._run, name="d4d-save", daemon=True)
+        self._thread.start()
+
+    def _run(self):
+        while True:
+            sample = self._q.get()
+            if sample is None:
+                return
+            if self._error is None:
+                try:
+                    self._save_fn(sample, self._output_dir)
+                except BaseException as e:  # noqa: BLE001 -- re-raised on the caller's thread
+                    self._error = e
+
+    def submit(self, sample: dict):
+        if self._error is not None:
+            raise self._error
+        self._q.put(sample)
+
+    def close(self):
+        self._q.put(None)
+        self._thread.join()
+        if self._error is not None:
+            raise self._error

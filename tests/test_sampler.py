@@ -117,3 +117,87 @@ def test_sampler_two_ranks_equal_single_process():
     for rank, lat, ti in results:
         torch.testing.assert_close(torch.tensor(lat), single.grid_latents, rtol=1e-5, atol=1e-5)
         assert torch.tensor(ti).equal(single.grid_timestep_indices)
+
+
+# ---- dataset prefetch and asynchronous save (host logic) ---------------------------------------
+def _grid_of(s):
+    return s.grid_latents.clone(), s.grid_timestep_indices.clone()
+
+
+@pytest.mark.parametrize("tag", ["v6_t4_stride1", "v5_t2_stride2_unidir"])
+def test_prefetch_and_async_save_change_nothing_but_the_overlap(tag):
+    """Same grid, same samples handed to ``save_fn`` in the same order as the sequential run (and therefore as the
+    reference sampler: the sequential run is pinned against it above)."""
+    c = torch.load(os.path.join(GOLD, "sampler_ref.pt"))["cases"][tag]
+    seq, ovl = [], []
+    a = _make(c["kwargs"], c["n_cams"], OraclePipeline(), save_fn=lambda sample, out_dir: seq.append(sample))
+    a.execute_tasks()
+    b = B200SlidingIterativeSampler(dataset=SyntheticSpaTemDataset(c["n_cams"]), pipelines=[OraclePipeline()], output_dir=None,
+                                    num_denoising_steps=1, guidance_scale=2.0, sliding_shift=0, prefetch=True, async_save=True,
+                                    save_fn=lambda sample, out_dir: ovl.append(sample), **c["kwargs"])
+    b.execute_tasks()
+    ga, gb = _grid_of(a), _grid_of(b)
+    assert torch.equal(ga[0], gb[0]) and torch.equal(ga[1], gb[1])
+    assert len(seq) == len(ovl) == sum(len(t) for t in a.all_tasks)
+    for x, y in zip(seq, ovl):
+        assert (x["alt"], x["domain"], x["domain_label"]) == (y["alt"], y["domain"], y["domain_label"])
+        assert torch.equal(x["result_latents"], y["result_latents"])
+        assert torch.equal(x["timestep_indices"], y["timestep_indices"])
+
+
+def test_prefetch_and_async_save_overlap_host_work_with_the_denoise():
+    """Dataset load, denoise and save take 60 ms each (sleeps = no GIL held, like PIL decode / CUDA waits / file writes):
+    sequentially 3 x 60 ms per task, overlapped about 60 ms per task."""
+    import time
+
+    class SlowDataset(SyntheticSpaTemDataset):
+        def get_item(self, **kw):
+            time.sleep(0.06)
+            return super().get_item(**kw)
+
+    class SlowPipeline(OraclePipeline):
+        def sliding_iterative_denoise(self, **kw):
+            time.sleep(0.06)
+            return super().sliding_iterative_denoise(**kw)
+
+    def slow_save(sample, out_dir):
+        time.sleep(0.06)
+
+    kwargs = dict(window_size=2, sliding_stride=1, bidirectional=True, alternation_rounds=1, spa_label_range=(0, 6, 1),
+                  tem_label_range=(0, 8, 1), input_spa_labels=(1, 4))
+
+    def run(overlap):
+        s = B200SlidingIterativeSampler(dataset=SlowDataset(6), pipelines=[SlowPipeline()], output_dir=None,
+                                        num_denoising_steps=1, guidance_scale=2.0, sliding_shift=0, save_fn=slow_save,
+                                        prefetch=overlap, async_save=overlap, **kwargs)
+        t0 = time.perf_counter()
+        s.execute_tasks()
+        return time.perf_counter() - t0, sum(len(t) for t in s.all_tasks)
+
+    t_seq, n = run(False)
+    t_ovl, _ = run(True)
+    assert n == 8
+    assert t_seq > n * 0.17                      # three 60 ms phases back to back
+    assert t_ovl < t_seq - 0.5 * n * 0.06, (t_seq, t_ovl)   # at least half of one phase per task hidden (ideal: two)
+
+
+def test_async_save_and_prefetch_errors_surface_on_the_caller():
+    c = torch.load(os.path.join(GOLD, "sampler_ref.pt"))["cases"]["v6_t4_stride1"]
+
+    def bad_save(sample, out_dir):
+        raise OSError("disk full")
+    s = B200SlidingIterativeSampler(dataset=SyntheticSpaTemDataset(c["n_cams"]), pipelines=[OraclePipeline()], output_dir=None,
+                                    num_denoising_steps=1, guidance_scale=2.0, sliding_shift=0, async_save=True,
+                                    save_fn=bad_save, **c["kwargs"])
+    with pytest.raises(OSError, match="disk full"):
+        s.execute_tasks()
+
+    class BadDataset(SyntheticSpaTemDataset):
+        def get_item(self, **kw):
+            if kw["tem_labels"] == ["000002"]:
+                raise FileNotFoundError("missing frame 000002")
+            return super().get_item(**kw)
+    s = B200SlidingIterativeSampler(dataset=BadDataset(c["n_cams"]), pipelines=[OraclePipeline()], output_dir=None,
+                                    num_denoising_steps=1, guidance_scale=2.0, sliding_shift=0, prefetch=True, **c["kwargs"])
+    with pytest.raises(FileNotFoundError, match="000002"):
+        s.execute_tasks()

@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--cams", type=int, default=48)
     ap.add_argument("--frames", type=int, default=16)
     ap.add_argument("--out", default="gpurun_out/grid.json")
+    ap.add_argument("--prefetch", action="store_true", help="load the next task's dataset item on a helper thread")
     args = ap.parse_args()
 
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
@@ -52,7 +53,8 @@ def main():
     inputs = [1, 13, 25, 37] if args.cams >= 48 else sorted({(args.cams * k) // 4 + 1 for k in range(4)})
     sampler = B200SlidingIterativeSampler(ds, [pipe], output_dir=None, spa_label_range=[0, args.cams, 1],
                                           tem_label_range=[0, args.frames, 1], input_spa_labels=inputs, window_size=12,
-                                          sliding_stride=1, bidirectional=False, alternation_rounds=3, guidance_scale=2.0)
+                                          sliding_stride=1, bidirectional=False, alternation_rounds=3, guidance_scale=2.0,
+                                          prefetch=args.prefetch)
 
     # count window steps and their device time (CUDA events around every denoise_window call)
     stats = {"spatial": [0, 0.0], "temporal": [0, 0.0]}
@@ -84,7 +86,7 @@ def main():
         "workload": f"demo_4d_tiny-shaped grid: {args.cams} cameras x {args.frames} frames @ {args.latent}x{args.latent} latents, "
                     "window 12 (+4 / +12 cond), stride 1, 3 alternation rounds, CFG 2.0, SD-2.1 UNet layout, random weights, "
                     "synthetic dataset, pooling stand-in for the VAE",
-        "n_gpus": world, "rank": rank,
+        "n_gpus": world, "rank": rank, "prefetch": bool(args.prefetch),
         "window_steps": {d: stats[d][0] for d in stats}, "frames_per_window": {d: sorted(frames.get(d, [])) for d in stats},
         "device_ms_in_denoise_window": {d: round(stats[d][1], 1) for d in stats},
         "ms_per_window_step": {d: round(stats[d][1] / max(1, stats[d][0]), 2) for d in stats},
