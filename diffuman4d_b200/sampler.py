@@ -28,6 +28,12 @@ the GPU idles during both.  With ``prefetch=True`` the dataset part of the NEXT 
 thread while the current task is on the GPU (the tasks of a round touch disjoint target cells, and the grid rows of a task
 are still gathered on the calling thread right before its denoise); with ``async_save=True`` ``save_fn`` runs on one
 worker thread in task order behind a bounded queue and its first exception is re-raised by ``execute_tasks``.
+
+Encoded-image cache (first step; opt-in ``cache_pixel_latents=True``): the reference VAE-encodes all frames
+of a task in every task (PIPE:208-214), i.e. every image of the grid once per round and the cond view of a temporal task T
+times more.  With the cache the encoded image latents live in a third device grid ``[V, T, 4, h, w]``; a task encodes only
+the cells not seen before and hands ``pixel_values_latents`` to the pipeline.  Note the semantics: the reference draws
+``latent_dist.sample()`` anew at every encode, the cache keeps the first draw of a cell for the whole run.
 """
 from __future__ import annotations
 
@@ -48,9 +54,12 @@ class B200SlidingIterativeSampler:
                  spa_labels: Optional[Sequence[int]] = None, tem_labels: Optional[Sequence[int]] = None,
                  input_spa_labels: Sequence[int] = (1, 13, 25, 37),
                  save_fn: Optional[Callable[[dict, Optional[str]], None]] = None, prefetch: bool = False,
-                 async_save: bool = False):
+                 async_save: bool = False, cache_pixel_latents: bool = False):
         self.dataset, self.pipelines, self.output_dir, self.save_fn = dataset, list(pipelines), output_dir, save_fn
-        self.prefetch, self.async_save = prefetch, async_save
+        self.prefetch, self.async_save, self.cache_pixel_latents = prefetch, async_save, cache_pixel_latents
+        self.grid_pixel_latents: Optional[torch.Tensor] = None      # [V, T, C, h, w] encoded images (cache_pixel_latents)
+        self._pixel_cached: set = set()                             # (view, frame) cells already encoded (host-side: no sync)
+        self.vae_images_encoded = 0                                 # images sent through the VAE encoder by the cache path
         self.window_size, self.sliding_stride, self.sliding_shift = window_size, sliding_stride, sliding_shift
         self.bidirectional, self.num_denoising_steps = bidirectional, num_denoising_steps
         self.alternation_rounds, self.guidance_scale = alternation_rounds, guidance_scale
@@ -164,13 +173,17 @@ class B200SlidingIterativeSampler:
     @torch.no_grad()
     def denoise(self, sample: dict, pipe_idx: int = 0) -> dict:
         pipeline = self.pipelines[pipe_idx]
+        extra = {}
+        if self.cache_pixel_latents and getattr(pipeline, "vae", None) is not None:
+            extra["pixel_values_latents"] = self._cached_pixel_latents(sample, pipeline)
         result = pipeline.sliding_iterative_denoise(
-            pixel_values=sample["pixel_values"], plucker_embeds=sample["plucker_embeds"], skeletons=sample["skeletons"],
+            pixel_values=None if extra else sample["pixel_values"], plucker_embeds=sample["plucker_embeds"],
+            skeletons=sample["skeletons"],
             cond_masks=sample["cond_masks"], latents=sample["latents"], domain=sample["domain"],
             timestep_indices=sample["timestep_indices"], window_size=self.window_size, sliding_stride=self.sliding_stride,
             sliding_shift=self.sliding_shift, bidirectional=self.bidirectional,
             num_denoising_steps=self.num_denoising_steps, alternation_rounds=self.alternation_rounds,
-            guidance_scale=self.guidance_scale)
+            guidance_scale=self.guidance_scale, **extra)
         lat = result["latents"]
         self._ensure_grid(lat)
         vi, ti = (t.to(self._grid_device) for t in sample["_cells"])
@@ -181,6 +194,25 @@ class B200SlidingIterativeSampler:
         sample["fully_denoised"] = result["fully_denoised"]
         sample["result_latents"] = lat
         return sample
+
+    def _cached_pixel_latents(self, sample: dict, pipeline) -> torch.Tensor:
+        """Encoded images of this task's cells: encode what the cache has not seen (PIPE:208-214 encodes everything)."""
+        vi, ti = sample["_cells"]
+        keys = list(zip(vi.tolist(), ti.tolist()))
+        missing = [k for k, key in enumerate(keys) if key not in self._pixel_cached]
+        dev = pipeline.device
+        if missing:
+            px = sample["pixel_values"][torch.tensor(missing)].to(dev, torch.bfloat16)
+            enc = pipeline.vae.encode_latents(px)
+            self.vae_images_encoded += len(missing)
+            if self.grid_pixel_latents is None:
+                V, T = len(self.spa_labels), len(self.tem_labels)
+                self.grid_pixel_latents = torch.zeros((V, T, *enc.shape[1:]), dtype=enc.dtype, device=enc.device)
+            mv, mt = vi[missing].to(enc.device), ti[missing].to(enc.device)
+            self.grid_pixel_latents.index_put_((mv, mt), enc)
+            self._pixel_cached.update(keys[k] for k in missing)
+        g = self.grid_pixel_latents
+        return g[vi.to(g.device), ti.to(g.device)]
 
     # ---- SAMP:192-214 -----------------------------------------------------------------------------------------
     def prepare_tasks(self):

@@ -201,3 +201,61 @@ def test_async_save_and_prefetch_errors_surface_on_the_caller():
                                     num_denoising_steps=1, guidance_scale=2.0, sliding_shift=0, prefetch=True, **c["kwargs"])
     with pytest.raises(FileNotFoundError, match="000002"):
         s.execute_tasks()
+
+
+# ---- SURVEY 8f row 1, first step: encoded-image cache across tasks -----------------------------------------------------
+class _CountingVAE:
+    def __init__(self):
+        self.images = 0
+
+    def encode_latents(self, x):
+        self.images += len(x)
+        z = F.avg_pool2d(x.float(), 8)
+        return torch.cat([z, z.mean(dim=1, keepdim=True)], dim=1)
+
+
+class _VaePipeline(OraclePipeline):
+    """OraclePipeline with the ``vae`` / ``device`` attributes and the ``pixel_values_latents`` argument of
+    ``B200Diffuman4DPipeline.sliding_iterative_denoise`` (images are rounded to bf16 before the encoder, as there)."""
+
+    def __init__(self):
+        super().__init__()
+        self.vae, self.device = _CountingVAE(), torch.device("cpu")
+
+    def sliding_iterative_denoise(self, pixel_values=None, pixel_values_latents=None, **kw):
+        if pixel_values_latents is None:
+            pixel_values_latents = self.vae.encode_latents(pixel_values.to(torch.bfloat16))
+        h, w = pixel_values_latents.shape[-2:]
+        mask = F.interpolate(kw["cond_masks"], size=(h, w), mode="nearest")
+        latents = kw["latents"]
+        if latents is None:
+            latents = torch.randn((len(pixel_values_latents), 4, h, w), generator=torch.Generator().manual_seed(9000 + self.calls))
+            self.calls += 1
+        out = sliding_iterative_denoise_oracle(
+            self.unet, DDIMOracle(SchedulerConfig()), pixel_latents=pixel_values_latents, plucker=kw["plucker_embeds"],
+            skeletons=kw["skeletons"], cond_mask=mask, latents=latents, domain=kw["domain"],
+            timestep_indices=kw["timestep_indices"].cpu(), window_size=kw["window_size"], sliding_stride=kw["sliding_stride"],
+            sliding_shift=kw["sliding_shift"], bidirectional=kw["bidirectional"], num_denoising_steps=kw["num_denoising_steps"],
+            alternation_rounds=kw["alternation_rounds"], guidance_scale=kw["guidance_scale"], enable_pose_encoder=True)
+        out["images"] = out["latents"]
+        return out
+
+
+def test_pixel_latent_cache_encodes_every_grid_cell_once():
+    c = torch.load(os.path.join(GOLD, "sampler_ref.pt"))["cases"]["v6_t4_stride1"]
+
+    def run(cache):
+        pipe = _VaePipeline()
+        s = B200SlidingIterativeSampler(dataset=SyntheticSpaTemDataset(c["n_cams"]), pipelines=[pipe], output_dir=None,
+                                        num_denoising_steps=1, guidance_scale=2.0, sliding_shift=0, cache_pixel_latents=cache,
+                                        **c["kwargs"])
+        s.execute_tasks()
+        return s, pipe
+    a, pa = run(False)
+    b, pb = run(True)
+    assert torch.equal(a.grid_latents, b.grid_latents) and torch.equal(a.grid_timestep_indices, b.grid_timestep_indices)
+    per_task = sum(len(a._fetch(**t)["labels"]) for tasks in a.all_tasks for t in tasks)
+    cells = len(a.spa_labels) * len(a.tem_labels)
+    assert pa.vae.images == per_task                       # the reference's behaviour: every frame of every task
+    assert pb.vae.images == b.vae_images_encoded == cells  # cached: every image of the grid once
+    assert cells < per_task
